@@ -1,0 +1,192 @@
+/*
+ * kliff_b200.h — C-ABI of libkliff_b200.so: the B200-native (sm_100a) replacement for the two
+ * native extensions that KLIFF's descriptor/NN hot path sits on:
+ *
+ *   kliff.neighbor.neighlist                 (kliff/neighbor/neighbor_list_bind.cpp:31-253 over
+ *                                             neighbor_list.h:24-53: nbl_create_paddings,
+ *                                             nbl_build, nbl_get_neigh)
+ *   kliff.legacy.descriptors.symmetry_function.sf
+ *                                            (sym_fn_bind.cpp:8-95 over sym_fn.hpp: Descriptor::
+ *                                             set_cutoff, add_descriptor, generate_one_atom)
+ * plus the force contraction of kliff/legacy/calculators/calculator_torch.py:266-269 and the
+ * dense fold of kliff/legacy/descriptors/symmetry_function/sym_fn.py:163-185.
+ *
+ * Where the reference FFI is called once per atom from a Python loop (sym_fn.py:155-160),
+ * these entry points are batch-level: one call covers all centre atoms of a configuration (or of
+ * many concatenated configurations).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; no torch / C++ types cross the boundary.
+ *   - pointers named d_* are DEVICE pointers owned by the caller; h_* are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void*; all device work is enqueued on it.  Calls that
+ *     must return a size to the host (…_begin, …_count) synchronise that stream once; all others
+ *     are asynchronous.
+ *   - scratch memory is taken from the CUDA stream-ordered allocator (cudaMallocAsync) on
+ *     `stream` and released before return or by the matching *_finish / *_destroy call.
+ *   - return value: 0 = ok; 1 = the reference's own error class for that call (singular cell,
+ *     atom collision / cell grid too large — what neighbor_list_bind.cpp:68-72,205-209 turn into
+ *     RuntimeError); other positive codes are KB_ERR_*; negative = -(cudaError_t).
+ *   - no global mutable state: every function may be called from any host thread; one CUDA
+ *     context (device) per process/rank is assumed.
+ */
+#ifndef KLIFF_B200_H_
+#define KLIFF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_OK 0
+#define KB_ERR_REFERENCE 1      /* singular cell / collision / cell grid too large */
+#define KB_ERR_INVALID 2        /* bad argument */
+#define KB_ERR_LIMIT 3          /* a compiled-in limit (KB_MAX_*) exceeded */
+#define KB_ERR_UNSUPPORTED 4    /* device is not sm_100 */
+
+#define KB_MAX_SPECIES 8
+#define KB_MAX_TWO 64           /* radial (g1,g2,g3) parameter sets */
+#define KB_MAX_GROUPS 32        /* angular groups: one (family, eta) each */
+#define KB_GROUP_WIDTH 8        /* (zeta, lambda) entries per angular group */
+
+/* Kinds, as in the reference's hyper-parameter dictionary keys (sym_fn.py:244-247). */
+#define KB_G1 1
+#define KB_G2 2
+#define KB_G3 3
+#define KB_G4 4
+#define KB_G5 5
+
+/*
+ * Descriptor definition = Descriptor::set_cutoff + add_descriptor state (sym_fn.cpp:71-106),
+ * regrouped for the GPU: radial sets are listed one by one; angular sets are grouped by
+ * (family, eta) so that the exponential is shared by up to KB_GROUP_WIDTH (zeta, lambda)
+ * entries.  `*_out` is the descriptor index (running sum of rows in family insertion order,
+ * sym_fn.cpp:96-100).  kliff_b200.legacy.descriptors builds this from the hyper-parameter dict.
+ */
+typedef struct kb_symfun_params
+{
+  int32_t n_species;
+  int32_t n_desc;                                  /* D */
+  int32_t n_two;
+  int32_t n_groups;
+  double rcut[KB_MAX_SPECIES * KB_MAX_SPECIES];    /* row-major [si][sj] */
+  int32_t two_kind[KB_MAX_TWO];                    /* KB_G1 / KB_G2 / KB_G3 */
+  int32_t two_out[KB_MAX_TWO];
+  double two_p0[KB_MAX_TWO];                       /* g2: eta,  g3: kappa */
+  double two_p1[KB_MAX_TWO];                       /* g2: Rs */
+  int32_t grp_kind[KB_MAX_GROUPS];                 /* KB_G4 / KB_G5 */
+  int32_t grp_n[KB_MAX_GROUPS];                    /* entries used, 1..KB_GROUP_WIDTH */
+  double grp_eta[KB_MAX_GROUPS];
+  double grp_zeta[KB_MAX_GROUPS][KB_GROUP_WIDTH];
+  double grp_lambda[KB_MAX_GROUPS][KB_GROUP_WIDTH];
+  int32_t grp_out[KB_MAX_GROUPS][KB_GROUP_WIDTH];
+  /* 1 when every group's entry e is (zeta, lambda) = ({1,2,4,16}[e/2], {-1,+1}[e%2]) with unused
+   * entries marked grp_out < 0 (set51/set30 and every Behler-style set): enables the
+   * multiplication-only power chain.  0 = generic pow(). */
+  int32_t canonical_zl;
+  int32_t reserved;
+} kb_symfun_params;
+
+/* ------------------------------------------------------------------------------------------ */
+const char* kb_version(void);
+const char* kb_error_string(int code);
+/* sm count / compute capability of the current device; KB_ERR_UNSUPPORTED unless cc 10.x */
+int kb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Padding (periodic image) atoms — replaces neighlist.create_paddings                        */
+/* (neighbor_list_bind.cpp:168-252 -> nbl_create_paddings neighbor_list.cpp:283-418).          */
+/* Output order and every coordinate bit match the reference: shift-major, atom-minor.         */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct kb_pad_plan kb_pad_plan;
+/* Counts paddings (synchronises once).  h_cell: 9 doubles, rows = lattice vectors; h_pbc: 3. */
+int kb_pad_begin(int32_t natoms, double cutoff, const double* h_cell, const int32_t* h_pbc,
+                 const double* d_coords, int64_t* h_npad, kb_pad_plan** plan, void* stream);
+/* Writes the paddings (asynchronous) and frees the plan. d_species may be NULL with
+ * d_pad_species NULL (species then follow from d_pad_image). */
+int kb_pad_finish(kb_pad_plan* plan, const int32_t* d_species, double* d_pad_coords,
+                  int32_t* d_pad_species, int32_t* d_pad_image, void* stream);
+void kb_pad_destroy(kb_pad_plan* plan, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Cell-list neighbor build — replaces NeighList.build + get_neigh                             */
+/* (neighbor_list_bind.cpp:41-146 -> nbl_build neighbor_list.cpp:78-243).                      */
+/* CSR over ALL ntot atoms (atoms with need == 0 get empty lists), each list sorted ascending  */
+/* ("canonical sorting"); as a set it equals the reference's list bit for bit.                 */
+/* half != 0 keeps only neighbors j > i (no reference counterpart; SURVEY.md §8a note i).      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct kb_nl_plan kb_nl_plan;
+/* d_need may be NULL: then atoms [0, n_need) need neighbors (contributing atoms first,
+ * kliff/neighbor/neighbor.py:101-104).  Writes d_counts[ntot], d_offsets[ntot+1]; returns the
+ * total number of indices and the longest list (synchronises once). */
+int kb_nl_begin(int32_t ntot, int32_t n_need, const double* d_coords, const int32_t* d_need,
+                double influence_distance, double cutoff, int32_t half, int32_t* d_counts,
+                int64_t* d_offsets, int64_t* h_total, int32_t* h_maxn, kb_nl_plan** plan,
+                void* stream);
+int kb_nl_finish(kb_nl_plan* plan, int32_t* d_indices, void* stream);
+void kb_nl_destroy(kb_nl_plan* plan, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Symmetry functions + dG/dr — replaces the per-atom loop over sf.Descriptor.generate_one_atom */
+/* (sym_fn.py:155-160 -> sym_fn_bind.cpp:38-94 -> sym_fn.cpp:416-602).                         */
+/*                                                                                            */
+/* Centre atom t (0 <= t < n_centers) is atom a = d_centers[t] (or t when d_centers == NULL);  */
+/* its neighbors are d_nl_indices[d_nl_offsets[a] .. d_nl_offsets[a+1]).                       */
+/* Outputs: d_zeta[t*D + d]; and, when d_dz != NULL, the reference's per-atom gradient block   */
+/* [D][n+1][3] (slot n = centre atom, sym_fn.hpp:188-191) stored at d_dz + d_dz_ptr[t].        */
+/* d_dz_ptr comes from kb_symfun_block_offsets: blocks are padded to 16 doubles (128 B).       */
+/* ------------------------------------------------------------------------------------------ */
+#define KB_SYMFUN_AUTO 0
+#define KB_SYMFUN_GENERAL 1     /* global-atomics kernel: any neighbor count */
+#define KB_SYMFUN_TILED 2       /* shared-memory kernel: n <= 64 */
+
+int kb_symfun_block_offsets(int32_t n_centers, const int32_t* d_centers,
+                            const int64_t* d_nl_offsets, int32_t n_desc, int64_t* d_dz_ptr,
+                            int64_t* h_total, void* stream);
+int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_centers,
+                      const int32_t* d_centers, const double* d_coords, const int32_t* d_species,
+                      const int64_t* d_nl_offsets, const int32_t* d_nl_indices, int32_t maxn,
+                      double* d_zeta, double* d_dz, const int64_t* d_dz_ptr, int32_t mode,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Chain-rule force assembly — replaces CalculatorTorch._compute_forces on the dense           */
+/* (N, D, 3N) tensor (calculator_torch.py:207-213, 266-269) by a contraction over the packed   */
+/* blocks:  F[image[a], c] -= sum_d dEdG[t, d] * dz_t[d, slot(a), c].                           */
+/* fwd accumulates into d_forces[n_atoms_out*3] (caller zeroes); bwd is its adjoint w.r.t.     */
+/* dEdG (needed because the loss differentiates through dE/dG, calculator_torch.py:200-202):   */
+/*   gdEdG[t, d] = - sum_{slot,c} gF[image[a], c] * dz_t[d, slot, c].                           */
+/* scale (nullable, [D]) multiplies dEdG / gdEdG per descriptor: the 1/stdev normalisation of  */
+/* kliff/legacy/descriptors/descriptor.py:187-194 folded into the contraction.                 */
+/* ------------------------------------------------------------------------------------------ */
+int kb_force_scatter_fwd(int32_t n_centers, const int32_t* d_centers, const int64_t* d_nl_offsets,
+                         const int32_t* d_nl_indices, const int32_t* d_image, int32_t n_desc,
+                         const double* d_dEdG, const double* d_scale, const double* d_dz,
+                         const int64_t* d_dz_ptr, double* d_forces, void* stream);
+int kb_force_scatter_bwd(int32_t n_centers, const int32_t* d_centers, const int64_t* d_nl_offsets,
+                         const int32_t* d_nl_indices, const int32_t* d_image, int32_t n_desc,
+                         const double* d_gF, const double* d_scale, const double* d_dz,
+                         const int64_t* d_dz_ptr, double* d_gdEdG, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Dense views for small configurations — what SymmetryFunction.transform returns             */
+/* (sym_fn.py:163-185).  d_dense_forces: [n_centers][D][3*n_contrib] (caller zeroes);          */
+/* d_dense_stress: [n_centers][D][6], Voigt 11,22,33,23,31,12.  Either may be NULL.            */
+/* ------------------------------------------------------------------------------------------ */
+int kb_dense_fold(int32_t n_centers, const int32_t* d_centers, const int64_t* d_nl_offsets,
+                  const int32_t* d_nl_indices, const int32_t* d_image, const double* d_coords,
+                  int32_t n_desc, int32_t n_contrib, const double* d_dz, const int64_t* d_dz_ptr,
+                  double* d_dense_forces, double* d_dense_stress, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Measurement helpers (bench.py): FP64 FMA peak of this device, TFLOP/s (2 flops per FMA),    */
+/* measured with an unrolled register-resident DFMA chain; and an HBM copy probe, GB/s.        */
+/* ------------------------------------------------------------------------------------------ */
+int kb_probe_fp64_peak(double* h_tflops, void* stream);
+int kb_probe_hbm_copy(size_t bytes, double* h_gbs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KLIFF_B200_H_ */

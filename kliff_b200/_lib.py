@@ -1,0 +1,108 @@
+"""ctypes binding of kliff_b200/csrc/libkliff_b200.so (the C-ABI of include/kliff_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present, the
+first call raises.  Build the library with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``kliff_b200/csrc/build.sh``.
+"""
+import ctypes as C
+import os
+
+KB_MAX_SPECIES = 8
+KB_MAX_TWO = 64
+KB_MAX_GROUPS = 32
+KB_GROUP_WIDTH = 8
+
+KB_OK, KB_ERR_REFERENCE, KB_ERR_INVALID, KB_ERR_LIMIT, KB_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+KB_SYMFUN_AUTO, KB_SYMFUN_GENERAL, KB_SYMFUN_TILED = 0, 1, 2
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libkliff_b200.so")
+
+
+class kb_symfun_params(C.Structure):
+    _fields_ = [
+        ("n_species", C.c_int32),
+        ("n_desc", C.c_int32),
+        ("n_two", C.c_int32),
+        ("n_groups", C.c_int32),
+        ("rcut", C.c_double * (KB_MAX_SPECIES * KB_MAX_SPECIES)),
+        ("two_kind", C.c_int32 * KB_MAX_TWO),
+        ("two_out", C.c_int32 * KB_MAX_TWO),
+        ("two_p0", C.c_double * KB_MAX_TWO),
+        ("two_p1", C.c_double * KB_MAX_TWO),
+        ("grp_kind", C.c_int32 * KB_MAX_GROUPS),
+        ("grp_n", C.c_int32 * KB_MAX_GROUPS),
+        ("grp_eta", C.c_double * KB_MAX_GROUPS),
+        ("grp_zeta", (C.c_double * KB_GROUP_WIDTH) * KB_MAX_GROUPS),
+        ("grp_lambda", (C.c_double * KB_GROUP_WIDTH) * KB_MAX_GROUPS),
+        ("grp_out", (C.c_int32 * KB_GROUP_WIDTH) * KB_MAX_GROUPS),
+        ("canonical_zl", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+# every symbol include/kliff_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "kb_version", "kb_error_string", "kb_device_info",
+    "kb_pad_begin", "kb_pad_finish", "kb_pad_destroy",
+    "kb_nl_begin", "kb_nl_finish", "kb_nl_destroy",
+    "kb_symfun_block_offsets", "kb_symfun_forward",
+    "kb_force_scatter_fwd", "kb_force_scatter_bwd", "kb_dense_fold",
+    "kb_probe_fp64_peak", "kb_probe_hbm_copy",
+]
+
+_lib = None
+
+
+class KliffB200Error(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = lib().kb_error_string(code).decode() if _lib is not None else str(code)
+        super().__init__(f"{where}: [{code}] {msg}")
+
+
+def lib():
+    """Load (once) and return the C-ABI library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "kliff_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.kb_version.restype = C.c_char_p
+    L.kb_error_string.restype = C.c_char_p
+    L.kb_error_string.argtypes = [C.c_int]
+    L.kb_device_info.argtypes = [C.POINTER(i32)] * 3
+    L.kb_pad_begin.argtypes = [i32, dbl, C.POINTER(dbl), C.POINTER(i32), vp, C.POINTER(i64),
+                               C.POINTER(vp), vp]
+    L.kb_pad_finish.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.kb_pad_destroy.argtypes = [vp, vp]
+    L.kb_pad_destroy.restype = None
+    L.kb_nl_begin.argtypes = [i32, i32, vp, vp, dbl, dbl, i32, vp, vp, C.POINTER(i64),
+                              C.POINTER(i32), C.POINTER(vp), vp]
+    L.kb_nl_finish.argtypes = [vp, vp, vp]
+    L.kb_nl_destroy.argtypes = [vp, vp]
+    L.kb_nl_destroy.restype = None
+    L.kb_symfun_block_offsets.argtypes = [i32, vp, vp, i32, vp, C.POINTER(i64), vp]
+    L.kb_symfun_forward.argtypes = [C.POINTER(kb_symfun_params), i32, vp, vp, vp, vp, vp, i32, vp,
+                                    vp, vp, i32, vp]
+    L.kb_force_scatter_fwd.argtypes = [i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.kb_force_scatter_bwd.argtypes = [i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.kb_dense_fold.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.kb_probe_fp64_peak.argtypes = [C.POINTER(dbl), vp]
+    L.kb_probe_hbm_copy.argtypes = [C.c_size_t, C.POINTER(dbl), vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int:  # default
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(code, where):
+    if code != KB_OK:
+        raise KliffB200Error(code, where)

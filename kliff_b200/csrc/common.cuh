@@ -1,0 +1,60 @@
+// Shared device/host helpers of libkliff_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "kliff_b200.h"
+
+#define KB_PI 3.1415926535897932  // the reference's literal (sym_fn.cpp:9)
+#define KB_TOL 1.0e-10            // neighbor_list.cpp:14
+
+#define KB_CUDA(call)                                                          \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess) return -(int) e_;                                   \
+  } while (0)
+
+#define KB_LAUNCH_CHECK()                                                      \
+  do {                                                                         \
+    cudaError_t e_ = cudaGetLastError();                                       \
+    if (e_ != cudaSuccess) return -(int) e_;                                   \
+  } while (0)
+
+static inline cudaStream_t kb_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+// ---- IEEE-exact, never-contracted double arithmetic --------------------------------------
+// The integer outputs (padding selection, neighbor sets) must equal the reference's bit for
+// bit, and the reference is built without FMA (x86-64 -O2).  nvcc contracts a*b+c into DFMA by
+// default, so every expression that feeds a predicate uses these.
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+// a0*b0 + a1*b1 + a2*b2 evaluated left to right (kliff/neighbor/helper.hpp:26-29)
+__device__ __forceinline__ double xdot3(double a0, double a1, double a2, double b0, double b1,
+                                        double b2)
+{
+  return xadd(xadd(xmul(a0, b0), xmul(a1, b1)), xmul(a2, b2));
+}
+// dx*dx + dy*dy + dz*dz (neighbor_list.cpp:197, sym_fn.cpp:447)
+__device__ __forceinline__ double xnorm2(double dx, double dy, double dz)
+{
+  return xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
+}
+
+// ---- device-wide exclusive scan (hand-written; used for pad counts, cell starts, CSR) -----
+template <typename Tin, typename Tout>
+int kb_exclusive_scan(const Tin* d_in, Tout* d_out, int64_t n, Tout* d_total /*nullable*/,
+                      cudaStream_t stream);
+
+// 64-bit shuffle helpers
+__device__ __forceinline__ double shfl_xor_d(double v, int m)
+{
+  return __shfl_xor_sync(0xffffffffu, v, m);
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += shfl_xor_d(v, m);
+  return v;
+}

@@ -1,0 +1,129 @@
+// Version / error strings / device info and the two measurement probes used by bench.py.
+#include "common.cuh"
+
+namespace {
+
+// 8 independent DFMA chains per thread, fully unrolled: measures the FP64 FMA pipe, not memory.
+__global__ void __launch_bounds__(256)
+dfma_probe_kernel(int iters, double seed, double* __restrict__ sink)
+{
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int it = 0; it < iters; it++)
+  {
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+    {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.6789) sink[0] = s;  // never true; keeps the chains alive
+}
+
+__global__ void __launch_bounds__(256)
+copy_probe_kernel(const double2* __restrict__ in, double2* __restrict__ out, size_t n)
+{
+  for (size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x; q < n;
+       q += (size_t) gridDim.x * blockDim.x)
+    out[q] = in[q];
+}
+
+}  // namespace
+
+extern "C" const char* kb_version(void) { return "kliff_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* kb_error_string(int code)
+{
+  switch (code)
+  {
+    case KB_OK: return "ok";
+    case KB_ERR_REFERENCE:
+      return "reference error class: singular cell, atom collision, or cell grid too large";
+    case KB_ERR_INVALID: return "invalid argument";
+    case KB_ERR_LIMIT: return "compiled-in limit exceeded";
+    case KB_ERR_UNSUPPORTED: return "device is not sm_100 (B200)";
+    default:
+      if (code < 0) return cudaGetErrorString((cudaError_t) (-code));
+      return "unknown error";
+  }
+}
+
+extern "C" int kb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor)
+{
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  KB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return prop.major == 10 ? KB_OK : KB_ERR_UNSUPPORTED;
+}
+
+extern "C" int kb_probe_fp64_peak(double* h_tflops, void* stream)
+{
+  if (!h_tflops) return KB_ERR_INVALID;
+  cudaStream_t st = kb_stream(stream);
+  int32_t sms = 0;
+  int rc = kb_device_info(&sms, nullptr, nullptr);
+  if (rc) return rc;
+  double* sink = nullptr;
+  KB_CUDA(cudaMallocAsync((void**) &sink, sizeof(double), st));
+  cudaEvent_t e0, e1;
+  KB_CUDA(cudaEventCreate(&e0));
+  KB_CUDA(cudaEventCreate(&e1));
+  const int blocks = sms * 8, iters = 4096;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++)
+  {
+    KB_CUDA(cudaEventRecord(e0, st));
+    dfma_probe_kernel<<<blocks, 256, 0, st>>>(iters, 1.0 + rep, sink);
+    KB_CUDA(cudaEventRecord(e1, st));
+    KB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    KB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * 16.0 * (double) iters * 256.0 * (double) blocks;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  KB_CUDA(cudaFreeAsync(sink, st));
+  *h_tflops = best;
+  return KB_OK;
+}
+
+extern "C" int kb_probe_hbm_copy(size_t bytes, double* h_gbs, void* stream)
+{
+  if (!h_gbs || bytes < 32) return KB_ERR_INVALID;
+  cudaStream_t st = kb_stream(stream);
+  const size_t n = bytes / 16;
+  double2 *a = nullptr, *b = nullptr;
+  KB_CUDA(cudaMallocAsync((void**) &a, n * 16, st));
+  KB_CUDA(cudaMallocAsync((void**) &b, n * 16, st));
+  KB_CUDA(cudaMemsetAsync(a, 0, n * 16, st));
+  cudaEvent_t e0, e1;
+  KB_CUDA(cudaEventCreate(&e0));
+  KB_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++)
+  {
+    KB_CUDA(cudaEventRecord(e0, st));
+    copy_probe_kernel<<<148 * 16, 256, 0, st>>>(a, b, n);
+    KB_CUDA(cudaEventRecord(e1, st));
+    KB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    KB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double gbs = 2.0 * (double) (n * 16) / (ms * 1e-3) / 1e9;
+    if (rep > 0 && gbs > best) best = gbs;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  KB_CUDA(cudaFreeAsync(a, st));
+  KB_CUDA(cudaFreeAsync(b, st));
+  *h_gbs = best;
+  return KB_OK;
+}

@@ -1,0 +1,184 @@
+// Chain-rule force assembly and dense views over the packed dG/dr blocks.
+//
+// kb_force_scatter_fwd replaces CalculatorTorch._compute_forces on the dense (N, D, 3N) tensor
+// (kliff/legacy/calculators/calculator_torch.py:207-213, 266-269):
+//     F[image[a], c] -= sum_d dEdG[t, d] * dz_t[d, slot(a), c]
+// kb_force_scatter_bwd is its adjoint w.r.t. dEdG (the loss back-propagates through dE/dG,
+// calculator_torch.py:200-202).  Both stream every block once: HBM-bound, 0.25 flop/byte.
+// One warp per centre atom; lanes own columns (slot, c) of the [D][3(n+1)] block so that every
+// row read is a coalesced 256-byte segment.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SC_WARPS = 8;
+constexpr int SC_COLS = 4;  // columns per lane per pass -> 128 columns (n <= 41) in one pass
+
+template <bool BWD>
+__global__ void __launch_bounds__(SC_WARPS * 32)
+force_scatter_kernel(int n_centers, const int32_t* __restrict__ centers,
+                     const int64_t* __restrict__ nl_off, const int32_t* __restrict__ nl_idx,
+                     const int32_t* __restrict__ image, int D, const double* __restrict__ vec_in,
+                     const double* __restrict__ scale, const double* __restrict__ dz,
+                     const int64_t* __restrict__ dz_ptr, double* __restrict__ out)
+{
+  extern __shared__ double wsm[];  // fwd: [SC_WARPS][D] weights
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = blockIdx.x * SC_WARPS + warp;
+  if (t >= n_centers) return;
+  const int a = centers ? centers[t] : t;
+  const int64_t off = nl_off[a];
+  const int n = (int) (nl_off[a + 1] - off);
+  const int row = 3 * (n + 1);
+  const double* blk = dz + dz_ptr[t];
+  double* w = wsm + warp * D;
+  if (!BWD)
+  {
+    for (int d = lane; d < D; d += 32)
+      w[d] = vec_in[(int64_t) t * D + d] * (scale ? scale[d] : 1.0);
+    __syncwarp();
+  }
+  for (int c0 = 0; c0 < row; c0 += 32 * SC_COLS)
+  {
+    int tgt[SC_COLS];
+    double g[SC_COLS], acc[SC_COLS];
+#pragma unroll
+    for (int u = 0; u < SC_COLS; u++)
+    {
+      const int col = c0 + u * 32 + lane;
+      tgt[u] = -1;
+      g[u] = 0.0;
+      acc[u] = 0.0;
+      if (col < row)
+      {
+        const int slot = col / 3, c = col - 3 * slot;
+        const int atom = slot < n ? nl_idx[off + slot] : a;  // last slot = centre atom
+        tgt[u] = 3 * image[atom] + c;
+        if (BWD) g[u] = vec_in[tgt[u]];
+      }
+    }
+    if (!BWD)
+    {
+      for (int d = 0; d < D; d++)
+      {
+        const double wd = w[d];
+        const double* rp = blk + (int64_t) d * row + c0 + lane;
+#pragma unroll
+        for (int u = 0; u < SC_COLS; u++)
+          if (tgt[u] >= 0) acc[u] += wd * rp[u * 32];
+      }
+#pragma unroll
+      for (int u = 0; u < SC_COLS; u++)
+        if (tgt[u] >= 0) atomicAdd(out + tgt[u], -acc[u]);
+    }
+    else
+    {
+      for (int d = 0; d < D; d++)
+      {
+        const double* rp = blk + (int64_t) d * row + c0 + lane;
+        double s = 0.0;
+#pragma unroll
+        for (int u = 0; u < SC_COLS; u++)
+          if (tgt[u] >= 0) s += g[u] * rp[u * 32];
+        s = warp_sum(s);
+        if (lane == 0)
+        {
+          double* o = out + (int64_t) t * D + d;
+          const double v = -s * (scale ? scale[d] : 1.0);
+          *o = (c0 == 0) ? v : (*o + v);
+        }
+      }
+    }
+  }
+}
+
+// Dense (N, D, 3N) and stress (N, D, 6) views, sym_fn.py:163-185.  One thread per (t, d);
+// slots are visited in list order, centre last — the reference's own accumulation order, so
+// the dense view is deterministic and needs no atomics.
+__global__ void __launch_bounds__(128)
+dense_fold_kernel(int n_centers, const int32_t* __restrict__ centers,
+                  const int64_t* __restrict__ nl_off, const int32_t* __restrict__ nl_idx,
+                  const int32_t* __restrict__ image, const double* __restrict__ coords, int D,
+                  int n_contrib, const double* __restrict__ dz, const int64_t* __restrict__ dz_ptr,
+                  double* __restrict__ dense, double* __restrict__ stress)
+{
+  const int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (int64_t) n_centers * D) return;
+  const int t = (int) (q / D), d = (int) (q - (int64_t) t * D);
+  const int a = centers ? centers[t] : t;
+  const int64_t off = nl_off[a];
+  const int n = (int) (nl_off[a + 1] - off);
+  const double* rp = dz + dz_ptr[t] + (int64_t) d * 3 * (n + 1);
+  double* drow = dense ? dense + ((int64_t) t * D + d) * 3 * n_contrib : nullptr;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int slot = 0; slot <= n; slot++)
+  {
+    const int atom = slot < n ? nl_idx[off + slot] : a;
+    const double gx = rp[3 * slot], gy = rp[3 * slot + 1], gz = rp[3 * slot + 2];
+    if (drow)
+    {
+      double* o = drow + 3 * image[atom];
+      o[0] += gx; o[1] += gy; o[2] += gz;
+    }
+    if (stress)
+    {
+      const double x = coords[3 * atom], y = coords[3 * atom + 1], z = coords[3 * atom + 2];
+      s[0] += gx * x; s[1] += gy * y; s[2] += gz * z;  // 11, 22, 33
+      s[3] += gy * z; s[4] += gz * x; s[5] += gx * y;  // 23, 31, 12
+    }
+  }
+  if (stress)
+    for (int v = 0; v < 6; v++) stress[((int64_t) t * D + d) * 6 + v] = s[v];
+}
+
+}  // namespace
+
+extern "C" int kb_force_scatter_fwd(int32_t n_centers, const int32_t* d_centers,
+                                    const int64_t* d_nl_offsets, const int32_t* d_nl_indices,
+                                    const int32_t* d_image, int32_t n_desc, const double* d_dEdG,
+                                    const double* d_scale, const double* d_dz,
+                                    const int64_t* d_dz_ptr, double* d_forces, void* stream)
+{
+  if (n_centers < 0 || n_desc < 1) return KB_ERR_INVALID;
+  if (n_centers == 0) return KB_OK;
+  const int nblk = (n_centers + SC_WARPS - 1) / SC_WARPS;
+  force_scatter_kernel<false><<<nblk, SC_WARPS * 32, sizeof(double) * SC_WARPS * n_desc,
+                                kb_stream(stream)>>>(n_centers, d_centers, d_nl_offsets,
+                                                     d_nl_indices, d_image, n_desc, d_dEdG, d_scale,
+                                                     d_dz, d_dz_ptr, d_forces);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" int kb_force_scatter_bwd(int32_t n_centers, const int32_t* d_centers,
+                                    const int64_t* d_nl_offsets, const int32_t* d_nl_indices,
+                                    const int32_t* d_image, int32_t n_desc, const double* d_gF,
+                                    const double* d_scale, const double* d_dz,
+                                    const int64_t* d_dz_ptr, double* d_gdEdG, void* stream)
+{
+  if (n_centers < 0 || n_desc < 1) return KB_ERR_INVALID;
+  if (n_centers == 0) return KB_OK;
+  const int nblk = (n_centers + SC_WARPS - 1) / SC_WARPS;
+  force_scatter_kernel<true><<<nblk, SC_WARPS * 32, sizeof(double) * SC_WARPS * n_desc,
+                               kb_stream(stream)>>>(n_centers, d_centers, d_nl_offsets,
+                                                    d_nl_indices, d_image, n_desc, d_gF, d_scale,
+                                                    d_dz, d_dz_ptr, d_gdEdG);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}
+
+extern "C" int kb_dense_fold(int32_t n_centers, const int32_t* d_centers,
+                             const int64_t* d_nl_offsets, const int32_t* d_nl_indices,
+                             const int32_t* d_image, const double* d_coords, int32_t n_desc,
+                             int32_t n_contrib, const double* d_dz, const int64_t* d_dz_ptr,
+                             double* d_dense_forces, double* d_dense_stress, void* stream)
+{
+  if (n_centers < 0 || n_desc < 1) return KB_ERR_INVALID;
+  if (n_centers == 0 || (!d_dense_forces && !d_dense_stress)) return KB_OK;
+  const int64_t items = (int64_t) n_centers * n_desc;
+  dense_fold_kernel<<<(unsigned) ((items + 127) / 128), 128, 0, kb_stream(stream)>>>(
+      n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, d_coords, n_desc, n_contrib, d_dz,
+      d_dz_ptr, d_dense_forces, d_dense_stress);
+  KB_LAUNCH_CHECK();
+  return KB_OK;
+}

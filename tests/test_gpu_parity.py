@@ -1,0 +1,316 @@
+"""Parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle, the recorded
+outputs of the unmodified reference C++ (tests/golden/ref_run_*.npz) and the reference's own
+known-answer vectors.  Bars: integer / coordinate outputs bit-exact; zeta and
+dG/dr <= 1e-10 max-norm-relative per (atom, descriptor) row; forces <= 1e-10 of max|F|."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, fams_from_npz, load_golden, rowwise_rel_err
+from kliff_b200 import _lib, ops
+from kliff_b200.legacy.descriptors.hyperparams import get_set30, get_set51
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+RUNS = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "ref_run_*.npz"))
+              if "mos2" not in p)
+KNAME = {1: "g1", 2: "g2", 3: "g3", 4: "g4", 5: "g5"}
+
+
+def hp_from_fams(fams):
+    from collections import OrderedDict
+    hp = OrderedDict()
+    for kind, v in fams:
+        if kind == 1:
+            hp["g1"] = None
+        elif kind == 2:
+            hp["g2"] = [{"eta": r[0], "Rs": r[1]} for r in v]
+        elif kind == 3:
+            hp["g3"] = [{"kappa": r[0]} for r in v]
+        else:
+            hp[KNAME[kind]] = [{"zeta": r[0], "lambda": r[1], "eta": r[2]} for r in v]
+    return hp
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    sm, major, minor = ops.device_info()
+    assert major == 10, "these kernels are built for sm_100a only"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def port():
+    return orc.Oracle("port")
+
+
+def gpu_neighbors(dev, cell, pbc, coords, z, infl, padding_need_neigh=False, half=False):
+    c = torch.tensor(np.ascontiguousarray(coords), dtype=torch.float64, device=dev)
+    zt = torch.tensor(np.ascontiguousarray(z), dtype=torch.int32, device=dev)
+    pc, ps, pi = ops.create_paddings(infl, cell, pbc, c, zt)
+    allc = torch.cat([c, pc]) if pc.shape[0] else c
+    n = c.shape[0]
+    need = None
+    if padding_need_neigh:
+        need = torch.ones(allc.shape[0], dtype=torch.int32, device=dev)
+    counts, offsets, indices, maxn = ops.build_neighbors(allc, n, infl, need=need, half=half)
+    image = torch.cat([torch.arange(n, dtype=torch.int32, device=dev), pi])
+    return dict(pc=pc, ps=ps, pi=pi, allc=allc, counts=counts, offsets=offsets, indices=indices,
+                maxn=maxn, image=image, n=n)
+
+
+def blocks_from_packed(dz, dz_ptr, counts, D):
+    dz = dz.cpu().numpy()
+    ptr = dz_ptr.cpu().numpy()
+    out = []
+    for t in range(len(ptr) - 1):
+        n = int(counts[t])
+        out.append(dz[ptr[t]:ptr[t] + 3 * D * (n + 1)].reshape(D, n + 1, 3))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+def test_kat_neighbor(dev):
+    """Reference tests/test_neighbor.py:37-64 through the GPU path."""
+    g = load_golden("ref_kat_neighbor.npz")
+    r = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], float(g["infl_dist"]))
+    assert np.allclose(r["allc"].cpu().numpy(), g["target_coords"])
+    assert np.array_equal(np.concatenate([g["z"], r["ps"].cpu().numpy()]), g["target_z"])
+    off = r["offsets"].cpu().numpy()
+    idx = r["indices"].cpu().numpy()
+    for i in range(4):
+        assert np.array_equal(idx[off[i]:off[i + 1]], np.sort(g["all_indices"][i]))
+    assert np.all(r["counts"].cpu().numpy()[4:] == 0)
+
+
+def test_kat_dimer(dev):
+    cell = np.eye(3) * 200.0
+    coords = np.array([[0.0, 0, 0], [2.0, 0, 0]])
+    for P in (1, 0):
+        r = gpu_neighbors(dev, cell, [P] * 3, coords, np.array([6, 8], np.int32), 5.0)
+        off = r["offsets"].cpu().numpy()
+        idx = r["indices"].cpu().numpy()
+        assert list(idx[off[0]:off[1]]) == [1] and list(idx[off[1]:off[2]]) == [0]
+        assert r["pc"].shape[0] == 0
+
+
+@pytest.mark.parametrize("name", RUNS + ["ref_run_mos2_neigh.npz"])
+def test_neighbors_bit_exact_vs_reference(dev, name):
+    g = load_golden(name)
+    infl = float(np.max(g["rcut"])) if "rcut" in g.files else float(g["infl_dist"])
+    r = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], infl)
+    assert np.array_equal(r["pc"].cpu().numpy(), g["pad_coords"])  # every coordinate bit
+    assert np.array_equal(r["ps"].cpu().numpy(), g["pad_z"])
+    assert np.array_equal(r["pi"].cpu().numpy(), g["pad_image"])
+    assert np.array_equal(r["counts"].cpu().numpy(), g["nl_counts"])
+    assert np.array_equal(r["offsets"].cpu().numpy(), g["nl_offsets"])
+    assert np.array_equal(r["indices"].cpu().numpy(), orc.canonical(g["nl_offsets"], g["nl_indices"]))
+    assert r["maxn"] == int(g["nl_counts"].max())
+
+
+def test_neighbors_padding_need_neigh_and_half(dev, port):
+    g = load_golden("ref_run_tri30_allfam.npz")
+    infl = float(np.max(g["rcut"]))
+    full = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], infl, padding_need_neigh=True)
+    allc = full["allc"].cpu().numpy()
+    oc, oo, oi = port.build_neighbors(allc, infl, np.ones(len(allc), np.int32))
+    assert np.array_equal(full["counts"].cpu().numpy(), oc)
+    assert np.array_equal(full["indices"].cpu().numpy(), orc.canonical(oo, oi))
+    half = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], infl, half=True)
+    hoff, hidx = half["offsets"].cpu().numpy(), half["indices"].cpu().numpy()
+    can = orc.canonical(g["nl_offsets"], g["nl_indices"])
+    for a in range(30):
+        ref = can[g["nl_offsets"][a]:g["nl_offsets"][a + 1]]
+        assert np.array_equal(hidx[hoff[a]:hoff[a + 1]], ref[ref > a])
+
+
+def test_neighbor_errors(dev):
+    bad = torch.tensor([[0.0, 0, 0], [1e-6, 0, 0], [1.0, 1, 1]], dtype=torch.float64, device=dev)
+    with pytest.raises(_lib.KliffB200Error) as e:
+        ops.build_neighbors(bad, 3, 3.0)
+    assert e.value.code == _lib.KB_ERR_REFERENCE
+    with pytest.raises(_lib.KliffB200Error) as e:
+        ops.create_paddings(3.0, np.zeros((3, 3)), [1, 1, 1], bad)
+    assert e.value.code == _lib.KB_ERR_REFERENCE
+    # empty input
+    counts, offsets, indices, maxn = ops.build_neighbors(bad[:0], 0, 3.0)
+    assert counts.numel() == 0 and indices.numel() == 0 and maxn == 0
+
+
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [_lib.KB_SYMFUN_TILED, _lib.KB_SYMFUN_GENERAL])
+@pytest.mark.parametrize("name", RUNS)
+def test_symfun_vs_recorded_reference(dev, port, name, mode):
+    g = load_golden(name)
+    fams = fams_from_npz(g)
+    infl = float(np.max(g["rcut"]))
+    r = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], infl)
+    n = r["n"]
+    code = torch.tensor(g["code"][r["image"].cpu().numpy()].astype(np.int32), device=dev)
+    P = ops.build_params(hp_from_fams(fams), g["rcut"])
+    zeta, dz, dz_ptr = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
+                                          n_centers=n, mode=mode)
+    zeta0, _, _ = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
+                                     n_centers=n, grad=False, mode=mode)
+    zh = zeta.cpu().numpy()
+    assert np.allclose(zh, g["zeta"], rtol=TOL, atol=TOL * np.abs(g["zeta"]).max(axis=0))
+    assert np.allclose(zeta0.cpu().numpy(), zh, rtol=1e-13, atol=1e-13 * np.abs(zh).max())
+    D = P.n_desc
+    counts = r["counts"].cpu().numpy()
+    blocks = blocks_from_packed(dz, dz_ptr, counts, D)
+    # recorded blocks use the reference's raw neighbor order; ours are ascending: permute slots
+    off = g["nl_offsets"]
+    for a in g["keep_atoms"]:
+        raw = g["nl_indices"][off[a]:off[a + 1]]
+        order = np.argsort(raw, kind="stable")
+        ref = np.concatenate([g[f"dz_{a}"][:, order, :], g[f"dz_{a}"][:, -1:, :]], axis=1)
+        assert rowwise_rel_err(blocks[a], ref) <= TOL, (name, a)
+    # all blocks at once through the force contraction with the recorded weights
+    w = torch.tensor(g["w"], device=dev)
+    pack = dict(offsets=r["offsets"], indices=r["indices"], image=r["image"], dz=dz, dz_ptr=dz_ptr,
+                D=D, n_out=n)
+    F = ops.force_scatter(w, pack).cpu().numpy().reshape(n, 3)
+    assert np.max(np.abs(F - g["forces_w"])) <= TOL * np.max(np.abs(g["forces_w"]))
+    # translation invariance: the slots of every (atom, descriptor) row sum to zero
+    for b in blocks:
+        s = np.abs(b.sum(axis=1)).max(axis=1)
+        assert np.all(s <= 1e-12 * np.maximum(np.abs(b).max(axis=(1, 2)), 1e-300))
+
+
+def test_kat_symmetry_function(dev):
+    """Reference tests/descriptors/test_symmetry_function.py:294-307 (np.allclose defaults):
+    zeta 8x9, dzetadr_forces[0] 9x24, dzetadr_stress[0] 9x6, through the dense-fold kernel."""
+    g = load_golden("ref_kat_symfun.npz")
+    fams = fams_from_npz(g)
+    rc = float(g["cutoff"])
+    r = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], rc)
+    n = r["n"]
+    code = torch.zeros(r["allc"].shape[0], dtype=torch.int32, device=dev)
+    P = ops.build_params(hp_from_fams(fams), np.array([[rc]]))
+    zeta, dz, dz_ptr = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
+                                          n_centers=n)
+    assert np.allclose(zeta.cpu().numpy(), g["zeta_ref"])
+    pack = dict(offsets=r["offsets"], indices=r["indices"], image=r["image"], dz=dz, dz_ptr=dz_ptr,
+                D=P.n_desc, n_out=n)
+    dense, stress = ops.dense_fold(pack, r["allc"], n, True, True)
+    assert np.allclose(dense[0].cpu().numpy(), g["dzetadr_forces_ref"])
+    assert np.allclose(stress[0].cpu().numpy(), g["dzetadr_stress_ref"])
+
+
+@pytest.mark.parametrize("hpname", ["set51", "set30"])
+def test_symfun_512_atoms_vs_oracle(dev, port, hpname):
+    """4x4x4 jittered diamond (512 atoms, 1 600+ paddings): every block against the oracle."""
+    hp = get_set51() if hpname == "set51" else get_set30()
+    rng = np.random.default_rng(5)
+    a, nx = 5.431, 4
+    basis = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0],
+                      [.25, .25, .25], [.25, .75, .75], [.75, .25, .75], [.75, .75, .25]])
+    cells = np.array([[i, j, k] for i in range(nx) for j in range(nx) for k in range(nx)])
+    pos = (cells[:, None, :] + basis[None]).reshape(-1, 3) * a + rng.normal(0, 0.05, (512, 3))
+    cell = np.eye(3) * a * nx
+    z = np.full(512, 14, np.int32)
+    r = gpu_neighbors(dev, cell, [1, 1, 1], pos, z, 5.0)
+    opc, ops_, opi = port.create_paddings(5.0, cell, [1, 1, 1], pos, z)
+    assert np.array_equal(opc, r["pc"].cpu().numpy())
+    allc = np.concatenate([pos, opc])
+    need = np.zeros(len(allc), np.int32); need[:512] = 1
+    oc, oo, oi = port.build_neighbors(allc, 5.0, need)
+    oi = orc.canonical(oo, oi)
+    assert np.array_equal(oi, r["indices"].cpu().numpy())
+    rc = np.array([[5.0]])
+    P = ops.build_params(hp, rc)
+    code = torch.zeros(len(allc), dtype=torch.int32, device=dev)
+    zeta, dz, dz_ptr = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
+                                          n_centers=512)
+    oz, og = port.symfun_range(rc, orc.fams_from_hyperparams(hp), 0, 512, allc,
+                               np.zeros(len(allc), np.int32), oo, oi)
+    assert np.max(np.abs(zeta.cpu().numpy() - oz) / np.abs(oz)) <= TOL
+    D = P.n_desc
+    blocks = blocks_from_packed(dz, dz_ptr, oc, D)
+    worst = 0.0
+    for t in range(512):
+        ref = og[3 * D * int(oo[t] + t):3 * D * int(oo[t + 1] + t + 1)].reshape(D, -1, 3)
+        worst = max(worst, rowwise_rel_err(blocks[t], ref))
+    assert worst <= TOL, worst
+    # padding of the packed layout is zero-filled and 128-byte aligned
+    ptr = dz_ptr.cpu().numpy()
+    assert np.all(ptr % 16 == 0)
+    dzh = dz.cpu().numpy()
+    for t in (0, 100, 511):
+        assert np.all(dzh[ptr[t] + 3 * D * (oc[t] + 1):ptr[t + 1]] == 0.0)
+
+
+def test_symfun_centers_subset_and_many_neighbors(dev, port):
+    """(a) an explicit centre list; (b) a dense lattice with n > 64 neighbors, which the tiled
+    kernel hands to the general kernel."""
+    rng = np.random.default_rng(9)
+    cell = np.eye(3) * 9.0
+    nx = 5
+    pos = (np.array([[i, j, k] for i in range(nx) for j in range(nx) for k in range(nx)]) + 0.5) * (9.0 / nx)
+    pos = pos + rng.normal(0, 0.05, pos.shape)
+    z = np.full(len(pos), 14, np.int32)
+    hp = get_set30()
+    rc = np.array([[5.0]])
+    r = gpu_neighbors(dev, cell, [1, 1, 1], pos, z, 5.0)
+    assert r["maxn"] > 64
+    allc = r["allc"].cpu().numpy()
+    off, idx = r["offsets"].cpu().numpy(), r["indices"].cpu().numpy()
+    P = ops.build_params(hp, rc)
+    code = torch.zeros(len(allc), dtype=torch.int32, device=dev)
+    centers = torch.tensor([3, 77, 124, 0], dtype=torch.int32, device=dev)
+    zeta, dz, dz_ptr = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
+                                          centers=centers)
+    D = P.n_desc
+    ptr = dz_ptr.cpu().numpy()
+    dzh = dz.cpu().numpy()
+    for t, a in enumerate(centers.cpu().numpy()):
+        nb = idx[off[a]:off[a + 1]]
+        oz, og = port.symfun_atom(rc, orc.fams_from_hyperparams(hp), a, allc,
+                                  np.zeros(len(allc), np.int32), nb)
+        assert np.max(np.abs(zeta[t].cpu().numpy() - oz) / np.abs(oz)) <= TOL
+        blk = dzh[ptr[t]:ptr[t] + 3 * D * (len(nb) + 1)].reshape(D, -1, 3)
+        assert rowwise_rel_err(blk, og) <= TOL
+
+
+def test_force_scatter_forward_backward(dev):
+    """fwd against numpy; bwd is the exact adjoint (<gF, fwd(w)> == <bwd(gF), w>), scale folds in;
+    autograd double-backward works (needed for create_graph=True training)."""
+    g = load_golden("ref_run_sic64_set51.npz")
+    fams = fams_from_npz(g)
+    r = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], float(np.max(g["rcut"])))
+    n = r["n"]
+    code = torch.tensor(g["code"][r["image"].cpu().numpy()].astype(np.int32), device=dev)
+    P = ops.build_params(hp_from_fams(fams), g["rcut"])
+    zeta, dz, dz_ptr = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
+                                          n_centers=n)
+    D = P.n_desc
+    rng = np.random.default_rng(2)
+    scale = torch.tensor(rng.uniform(0.5, 2.0, D), device=dev)
+    pack = dict(offsets=r["offsets"], indices=r["indices"], image=r["image"], dz=dz, dz_ptr=dz_ptr,
+                D=D, n_out=n, scale=scale)
+    w = torch.tensor(rng.normal(size=(n, D)), device=dev, requires_grad=True)
+    F = ops.force_scatter(w, pack)
+    counts = r["counts"].cpu().numpy()
+    blocks = blocks_from_packed(dz, dz_ptr, counts, D)
+    off, idx = r["offsets"].cpu().numpy(), r["indices"].cpu().numpy()
+    lists = [idx[off[t]:off[t + 1]] for t in range(n)]
+    Fo = orc.forces_sparse(w.detach().cpu().numpy() * scale.cpu().numpy(), blocks, lists,
+                           r["image"].cpu().numpy(), n)
+    assert np.max(np.abs(F.detach().cpu().numpy() - Fo)) <= 1e-12 * np.max(np.abs(Fo))
+    gF = torch.tensor(rng.normal(size=3 * n), device=dev)
+    (gw,) = torch.autograd.grad(F, w, gF, create_graph=True)
+    lhs = float((gF * F.detach()).sum())
+    rhs = float((gw.detach() * w.detach()).sum())
+    assert abs(lhs - rhs) <= 1e-11 * abs(lhs)
+    # double backward: d/d(gF) of <gw, v> = fwd(v)
+    gF2 = gF.clone().requires_grad_(True)
+    gw2 = ops._ForceGather.apply(gF2, pack)
+    v = torch.tensor(rng.normal(size=(n, D)), device=dev)
+    (back,) = torch.autograd.grad(gw2, gF2, v)
+    assert torch.allclose(back, ops.force_scatter(v, pack), rtol=1e-12, atol=1e-12)
