@@ -197,8 +197,9 @@ symfun_tiled_kernel(const __grid_constant__ kb_symfun_params P, const TiledArgs 
       }
       if (hit4)
       {
-        atomicOr(&ADJ4[j], 1ull << k);
-        atomicOr(&ADJ4[k], 1ull << j);
+        unsigned* a32 = reinterpret_cast<unsigned*>(ADJ4);  // native 32-bit ATOMS.OR
+        atomicOr(a32 + 2 * j + (k >> 5), 1u << (k & 31));
+        atomicOr(a32 + 2 * k + (j >> 5), 1u << (j & 31));
       }
     }
   }
@@ -337,12 +338,12 @@ symfun_tiled_kernel(const __grid_constant__ kb_symfun_params P, const TiledArgs 
 #pragma unroll
         for (int e = 0; e < GW; e++)
         {
-          phi[e] += C[e] * eF;
+          phi[e] = fma(C[e], eF, phi[e]);
           if (GRAD)
           {
-            acc[e][0] += Cp[e] * v1x + C[e] * v2x;
-            acc[e][1] += Cp[e] * v1y + C[e] * v2y;
-            acc[e][2] += Cp[e] * v1z + C[e] * v2z;
+            acc[e][0] = fma(C[e], v2x, fma(Cp[e], v1x, acc[e][0]));
+            acc[e][1] = fma(C[e], v2y, fma(Cp[e], v1y, acc[e][1]));
+            acc[e][2] = fma(C[e], v2z, fma(Cp[e], v1z, acc[e][2]));
           }
         }
       }

@@ -1,0 +1,1 @@
+"""Mirror of the `kliff.legacy` namespace for the descriptor / neural-network path."""

@@ -1,0 +1,361 @@
+"""`CalculatorTorch` / `CalculatorTorchSeparateSpecies` with the interface of
+kliff/legacy/calculators/calculator_torch.py:16-525.
+
+What changes underneath:
+  * `create()` runs the descriptor kernels once for all configurations and keeps the packed
+    result on the GPU (kliff_b200/packed.py); the fingerprints pickle is still written in the
+    reference's per-example format (zeta, energy, forces, ...), so `reuse=True` works.
+  * `compute(batch)` evaluates the MLP with torch (cuBLAS) on the resident, normalised zeta and
+    replaces the per-configuration dense `-tensordot(dE/dzeta, dzetadr_forces)`
+    (calculator_torch.py:207-213, 266-269) by ONE launch of the force-scatter kernel per batch,
+    differentiable through dE/dzeta (create_graph=True, :200-202).  The return value keeps the
+    reference's type: dict of lists of per-configuration tensors.
+  * `gpu=None` (the README call `CalculatorTorch(model)`) selects the process's CUDA device:
+    there is no CPU path.
+"""
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+from ...dataset.dataset_torch import FingerprintsDataset, fingerprints_collate_fn
+from ...packed import PackedFingerprints, PackedGradient
+from ...utils import default_device, pickle_load, to_path
+
+
+class CalculatorTorchError(Exception):
+    def __init__(self, msg):
+        super().__init__(msg)
+        self.msg = msg
+
+
+def _get_device(gpu):
+    """calculator_torch.py:582-594, minus the CPU branch."""
+    if gpu is None or isinstance(gpu, bool):
+        return default_device()
+    return torch.device("cuda", int(gpu))
+
+
+def _runs(indices):
+    """Split a list of configuration indices into maximal runs of consecutive integers."""
+    runs, start, prev = [], None, None
+    for pos, i in enumerate(indices):
+        if start is None:
+            start, prev, p0 = i, i, pos
+        elif i == prev + 1:
+            prev = i
+        else:
+            runs.append((start, prev + 1, p0))
+            start, prev, p0 = i, i, pos
+    if start is not None:
+        runs.append((start, prev + 1, p0))
+    return runs
+
+
+class CalculatorTorch:
+    implemented_property = ["energy", "forces", "stress"]
+
+    def __init__(self, model, gpu=None):
+        device = _get_device(gpu)
+        self._model = model.to(device)
+        self.dtype = self.model.descriptor.dtype
+        self.fingerprints_path = None
+        self.use_energy = None
+        self.use_forces = None
+        self.use_stress = None
+        self.results = dict([(i, None) for i in self.implemented_property])
+        self._packed = None
+        self._ref = None
+
+    # ------------------------------------------------------------------ create (:41-126)
+    def create(self, configs, use_energy=True, use_forces=True, use_stress=False,
+               fingerprints_filename="fingerprints.pkl", fingerprints_mean_stdev_filename=None,
+               reuse=False, use_welford_method=False, nprocs=1):
+        self.configs = configs
+        self.use_energy = use_energy
+        self.use_forces = use_forces
+        self.use_stress = use_stress
+        if not isinstance(configs, (list, tuple)):
+            configs = [configs]
+        desc = self.model.descriptor
+        if reuse:
+            self.fingerprints_path = to_path(fingerprints_filename)
+            if not self.fingerprints_path.exists():
+                raise CalculatorTorchError(
+                    f"You specified `reuse=True` to reuse the fingerprints stored in "
+                    f"`{self.fingerprints_path}` This file does not exists.")
+            if desc.normalize:
+                path = None if fingerprints_mean_stdev_filename is None else to_path(fingerprints_mean_stdev_filename)
+                if path is None or not path.exists():
+                    raise CalculatorTorchError(
+                        f"You specified `reuse=True` to reuse the fingerprints. The "
+                        f"mean and stdev file of the fingerprints `{path}` does not exists.")
+                desc.load_state_dict(pickle_load(path))
+            self._packed = None
+        else:
+            self.fingerprints_path = desc.generate_fingerprints(
+                configs, use_forces, use_stress, fingerprints_filename,
+                fingerprints_mean_stdev_filename, use_welford_method, nprocs)
+            self._packed = desc.packed_fingerprints
+        self.fingerprints_dataset = FingerprintsDataset(self.fingerprints_path)
+        if self._packed is None:
+            self._packed = self._packed_from_samples(self.fingerprints_dataset.fp)
+        self._upload_references()
+
+    def _packed_from_samples(self, samples):
+        """Rebuild the device store from a loaded pickle when its examples carry PackedGradient
+        objects; dense (reference-made) examples are served by the dense branch of compute()."""
+        if not samples or not self.use_forces:
+            return None
+        if not all(isinstance(s.get("dzetadr_forces"), PackedGradient) for s in samples):
+            return None
+        dev = self.model.device
+        packed = PackedFingerprints.from_packed_gradients(
+            self.model.descriptor.get_size(), dev, [s["dzetadr_forces"] for s in samples])
+        zeta = np.concatenate([np.asarray(s["zeta"], np.float64) for s in samples])
+        packed.zeta_normalized = torch.as_tensor(zeta, device=dev)
+        packed.scale = None  # gradients on disk are already divided by stdev
+        return packed
+
+    def _upload_references(self):
+        """Reference energies / forces / weights of every configuration, resident on the GPU for
+        the vectorised loss (kliff_b200/legacy/loss.py)."""
+        self._ref = None
+        if self._packed is None:
+            return
+        fp = self.fingerprints_dataset.fp
+        dev, dt = self.model.device, self.model.dtype
+        try:
+            e = np.array([float(s["energy"]) for s in fp]) if self.use_energy else np.zeros(len(fp))
+            f = (np.concatenate([np.asarray(s["forces"], np.float64).reshape(-1) for s in fp])
+                 if self.use_forces else np.zeros(0))
+        except Exception:
+            return
+        self._ref = dict(energy=torch.as_tensor(e, device=dev).to(dt),
+                         forces=torch.as_tensor(f, device=dev).to(dt))
+
+    # ------------------------------------------------------------------ small API (:128-159)
+    def get_fingerprints(self):
+        return self.fingerprints_dataset.fp
+
+    def get_compute_arguments(self, batch_size=1):
+        return DataLoader(dataset=self.fingerprints_dataset, batch_size=batch_size,
+                          collate_fn=fingerprints_collate_fn)
+
+    def set_fingerprints(self, fingerprints):
+        self.fingerprints_dataset.fp = fingerprints
+
+    def fit(self):
+        self.model.fit(self.fingerprints_path)
+
+    # ------------------------------------------------------------------ compute (:161-228)
+    def _model_energy(self, zeta, cfg_indices):
+        """Per-atom energies [N, 1] for stacked zeta; overridden for per-species models."""
+        return self.model(zeta)
+
+    def _packed_usable(self, batch):
+        if self._packed is None:
+            return False
+        P = self._packed
+        for s in batch:
+            i = s.get("index")
+            if i is None or i < 0 or i >= P.n_configs:
+                return False
+            lo, hi = P.config_slice(i)
+            if hi - lo != len(s["zeta"]):
+                return False
+        return True
+
+    def compute_packed(self, cfg_indices, want_forces=None):
+        """Vectorised core: energies [B] and flat forces [3 * atoms in batch] (both in the model
+        dtype, differentiable w.r.t. the model parameters) for configurations `cfg_indices`,
+        plus the per-configuration atom counts."""
+        P = self._packed
+        dev, dt = self.model.device, self.model.dtype
+        want_forces = self.use_forces if want_forces is None else want_forces
+        runs = _runs(list(cfg_indices))
+        spans = [(int(P.cfg_ptr[a]), int(P.cfg_ptr[b])) for a, b, _ in runs]
+        zparts = [P.zeta_normalized[lo:hi] for lo, hi in spans]
+        zeta = (zparts[0] if len(zparts) == 1 else torch.cat(zparts)).to(dt)
+        if want_forces:
+            zeta = zeta.detach().requires_grad_(True)
+        natoms = np.array([int(P.cfg_ptr[i + 1] - P.cfg_ptr[i]) for i in cfg_indices], np.int64)
+        cfg_of_atom = torch.repeat_interleave(
+            torch.arange(len(natoms), device=dev), torch.as_tensor(natoms, device=dev))
+        e_atom = self._model_energy(zeta, cfg_indices).reshape(-1)
+        energy = torch.zeros(len(natoms), dtype=dt, device=dev).index_add(0, cfg_of_atom, e_atom)
+        forces = None
+        if want_forces:
+            dedz = torch.autograd.grad(e_atom.sum(), zeta, create_graph=True)[0]
+            pieces, pos = [], 0
+            for lo, hi in spans:
+                f = P.forces(dedz[pos:pos + (hi - lo)].to(torch.float64), lo, hi)
+                pieces.append(f)
+                pos += hi - lo
+            forces = (pieces[0] if len(pieces) == 1 else torch.cat(pieces)).to(dt)
+        return energy, forces, natoms
+
+    def compute(self, batch):
+        grad = self.use_forces or self.use_stress
+        if self._packed_usable(batch) and not self.use_stress:
+            idx = [s["index"] for s in batch]
+            energy, forces, natoms = self.compute_packed(idx)
+            energy_config = list(energy.unbind(0))
+            forces_config = None
+            if self.use_forces:
+                forces_config = list(torch.split(forces, [3 * int(n) for n in natoms]))
+            stress_config = None
+        else:
+            energy_config, forces_config, stress_config = self._compute_dense(batch, grad)
+        self.results["energy"] = energy_config
+        self.results["forces"] = forces_config
+        self.results["stress"] = stress_config
+        return {"energy": energy_config, "forces": forces_config, "stress": stress_config}
+
+    def _compute_dense(self, batch, grad):
+        """Compatibility branch for fingerprints that carry dense (N, D, 3N) arrays (a cache
+        written by the reference, or `fingerprints_format = "dense"`): the reference's own
+        formulation, evaluated by torch on the GPU."""
+        device = self.model.device
+        zeta_config = [s["zeta"] for s in batch]
+        zeta = torch.cat(zeta_config, dim=0).to(device)
+        if grad:
+            zeta.requires_grad_(True)
+        e_atom = self._model_energy(zeta, [s.get("index", -1) for s in batch])
+        natoms = [len(z) for z in zeta_config]
+        energy_config = [e.sum() for e in torch.split(e_atom, natoms)]
+        forces_config = [] if self.use_forces else None
+        stress_config = [] if self.use_stress else None
+        if grad:
+            dedz_all = torch.autograd.grad(e_atom.sum(), zeta, create_graph=True)[0]
+            for s, dedz in zip(batch, torch.split(dedz_all, natoms)):
+                if self.use_forces:
+                    dzf = s["dzetadr_forces"]
+                    if isinstance(dzf, PackedGradient):
+                        dzf = torch.from_numpy(dzf.to_dense())
+                    forces_config.append(self._compute_forces(dedz, dzf.to(device)))
+                if self.use_stress:
+                    vol = s["volume"].to(device) if torch.is_tensor(s["volume"]) else s["volume"]
+                    stress_config.append(self._compute_stress(dedz, s["dzetadr_stress"].to(device), vol))
+        return energy_config, forces_config, stress_config
+
+    @staticmethod
+    def _compute_forces(denergy_dzeta, dzetadr):
+        return -torch.tensordot(denergy_dzeta, dzetadr, dims=([0, 1], [0, 1]))
+
+    @staticmethod
+    def _compute_stress(denergy_dzeta, dzetadr, volume):
+        return torch.tensordot(denergy_dzeta, dzetadr, dims=([0, 1], [0, 1])) / volume
+
+    # ------------------------------------------------------------------ model access (:230-353)
+    @property
+    def model(self):
+        return self._model
+
+    def save_model(self, epoch, force_save=False):
+        m = self.model
+        path = to_path(m.save_prefix).joinpath(f"model_epoch{epoch}.pkl")
+        if force_save or (epoch >= m.save_start and (epoch - m.save_start) % m.save_frequency == 0):
+            m.save(path)
+
+    def get_energy(self, batch):
+        return self.results["energy"]
+
+    def get_forces(self, batch):
+        return self.results["forces"]
+
+    def get_stress(self, batch):
+        return self.results["stress"]
+
+    def get_size_opt_params(self):
+        sizes, nelements = [], []
+        for p in self.model.parameters():
+            sizes.append(p.size())
+            nelements.append(int(np.prod(p.size())))
+        return sizes, nelements, sum(nelements)
+
+    def get_num_opt_params(self):
+        return self.get_size_opt_params()[-1]
+
+    def get_opt_params(self, flat=True):
+        params = []
+        for p in self.model.parameters():
+            if flat:
+                params = np.append(params, p.data.cpu().numpy().flatten())
+            else:
+                params.append(p)
+        return params
+
+    def update_model_params(self, parameters):
+        sizes, nelems, _ = self.get_size_opt_params()
+        idx = np.append(0, np.cumsum(nelems)).astype(int)
+        for ii, p in enumerate(self.model.parameters()):
+            chunk = np.asarray(parameters[idx[ii]:idx[ii + 1]]).reshape(tuple(sizes[ii]))
+            p.data = torch.as_tensor(chunk, dtype=p.dtype, device=p.device)
+
+
+class _ModelWrapper(torch.nn.Module):
+    """calculator_torch.py:499-525."""
+
+    def __init__(self, models):
+        super().__init__()
+        self._models = torch.nn.ModuleDict(models)
+        self._descriptor = list(models.values())[0].descriptor
+        self._dtype = list(models.values())[0].dtype
+
+    device = property(lambda self: next(self.parameters()).device)
+    descriptor = property(lambda self: self._descriptor)
+    dtype = property(lambda self: self._dtype)
+
+
+class CalculatorTorchSeparateSpecies(CalculatorTorch):
+    """One MLP per species (calculator_torch.py:356-496).  The reference buckets atoms in a
+    Python loop and differentiates once per configuration (:404-449); here the species of every
+    resident atom is a device tensor and one autograd pass covers the batch."""
+
+    def __init__(self, models, gpu=None):
+        device = _get_device(gpu)
+        self.models = models
+        self.dtype = None
+        for s, m in self.models.items():
+            m.to(device)
+            if self.dtype is None:
+                self.dtype = m.descriptor.dtype
+            elif self.dtype != m.descriptor.dtype:
+                raise CalculatorTorchError("inconsistent `dtype` from descriptors.")
+        self._model = _ModelWrapper(models)
+        self.fingerprints_path = None
+        self.use_energy = self.use_forces = self.use_stress = None
+        self.results = dict([(i, None) for i in self.implemented_property])
+        self._packed = None
+        self._ref = None
+        self._species_of_cfg = None
+
+    def create(self, configs, *args, **kwargs):
+        super().create(configs, *args, **kwargs)
+        names = list(self.models.keys())
+        self._species_names = names
+        per_cfg = []
+        for s in self.fingerprints_dataset.fp:
+            sp = s["configuration"].species
+            for x in sp:
+                if x not in self.models:
+                    raise CalculatorTorchError(f"No model for species: {x}")
+            per_cfg.append(torch.as_tensor([names.index(x) for x in sp], device=self.model.device))
+        self._species_of_cfg = per_cfg
+
+    def _model_energy(self, zeta, cfg_indices):
+        if self._species_of_cfg is None or any(i is None or i < 0 for i in cfg_indices):
+            raise CalculatorTorchError("per-species evaluation needs samples created by this calculator")
+        sp = torch.cat([self._species_of_cfg[i] for i in cfg_indices])
+        e_atom = torch.zeros((zeta.shape[0], 1), dtype=zeta.dtype, device=zeta.device)
+        for code, name in enumerate(self._species_names):
+            rows = torch.nonzero(sp == code, as_tuple=False).reshape(-1)
+            if rows.numel():
+                e_atom = e_atom.index_add(0, rows, self.models[name](zeta.index_select(0, rows)))
+        return e_atom
+
+    def save_model(self, epoch, force_save=False):
+        for name, m in self.models.items():
+            path = to_path(m.save_prefix).joinpath(f"model_{name}_epoch{epoch}.pkl")
+            if force_save or (epoch >= m.save_start and (epoch - m.save_start) % m.save_frequency == 0):
+                m.save(path)

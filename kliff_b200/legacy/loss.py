@@ -1,0 +1,300 @@
+"""`Loss` / `LossNeuralNetworkModel` with the interface of kliff/legacy/loss.py:37-223, 637-935
+(the neural-network half; physics-model losses are out of scope).
+
+Semantics kept: per configuration  residual = config_weight * (pred - ref), residual[0] *=
+energy_weight, residual[1:] *= forces_weight, residual /= natoms; loss = sum residual^2;
+batch loss = sum / len(batch); epoch loss = sum of batch losses; `optimizer.step(closure)`;
+the same `Epoch = ...  loss = ...` print-out and the extra loss pass after the last epoch.
+
+With the default residual function and a calculator that holds packed fingerprints the batch
+loss is evaluated in vectorised form on the GPU (one MLP pass, one force-scatter launch, one
+reduction) instead of the reference's per-configuration Python loop (loss.py:867-877); any
+user-supplied `residual_fn` takes the reference's per-configuration route.
+
+Data-parallel training: when torch.distributed is initialised every rank takes a contiguous
+1/world share of each batch, and the parameter gradients (641 numbers for 51-10-10-1) and the
+loss are all-reduced (NCCL over NVLink on the GPU box, gloo in the CPU tests) before the
+optimizer step, so all ranks follow the single-GPU trajectory up to summation order.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .calculators.calculator_torch import CalculatorTorch
+
+
+class LossError(Exception):
+    def __init__(self, msg):
+        super().__init__(msg)
+        self.msg = msg
+
+
+def energy_forces_residual(identifier, natoms, weight, prediction, reference, data):
+    """loss.py:37-110."""
+    residual = weight.config_weight * (prediction - reference)
+    residual[0] *= weight.energy_weight
+    residual[1:] *= weight.forces_weight
+    if data["normalize_by_natoms"]:
+        residual /= natoms
+    return residual
+
+
+def energy_residual(identifier, natoms, weight, prediction, reference, data):
+    """loss.py:113-138."""
+    residual = weight.config_weight * weight.energy_weight * (prediction - reference)
+    if data["normalize_by_natoms"]:
+        residual /= natoms
+    return residual
+
+
+def forces_residual(identifier, natoms, weight, prediction, reference, data):
+    """loss.py:141-166."""
+    residual = weight.config_weight * weight.forces_weight * (prediction - reference)
+    if data["normalize_by_natoms"]:
+        residual /= natoms
+    return residual
+
+
+def _check_residual_data(data, default):
+    if data is not None:
+        for key, value in data.items():
+            if key not in default:
+                raise LossError(
+                    f"Expect the keys of `residual_data` to be one or combinations of "
+                    f"{', '.join(default.keys())}; got {key}. ")
+            default[key] = value
+    return default
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+class Loss:
+    """Factory (loss.py:169-223): torch calculators get the neural-network loss."""
+
+    def __new__(cls, calculator, nprocs=1, residual_fn=None, residual_data=None,
+                log_per_atom_pred=False, log_per_atom_pred_path=None):
+        if isinstance(calculator, CalculatorTorch):
+            return LossNeuralNetworkModel(calculator, nprocs, residual_fn, residual_data,
+                                          log_per_atom_pred, log_per_atom_pred_path)
+        raise LossError("kliff_b200 only implements the loss of torch (neural-network) calculators; "
+                        "physics-motivated models are outside the accelerated path.")
+
+
+class LossNeuralNetworkModel:
+    torch_minimize_methods = ["Adadelta", "Adagrad", "Adam", "SparseAdam", "Adamax", "ASGD",
+                              "LBFGS", "RMSprop", "Rprop", "SGD"]
+
+    def __init__(self, calculator, nprocs=1, residual_fn=None, residual_data=None,
+                 log_per_atom_pred=False, log_per_atom_pred_path=None):
+        self.residual_data = _check_residual_data(residual_data, {"normalize_by_natoms": True})
+        self.calculator = calculator
+        self.nprocs = nprocs
+        self._default_residual = residual_fn is None
+        self.residual_fn = energy_forces_residual if residual_fn is None else residual_fn
+        self.optimizer = None
+        self.optimizer_state_path = None
+        if log_per_atom_pred:
+            raise LossError("log_per_atom_pred needs lmdb, which is not part of the accelerated path")
+        self.log_predictions = False
+        self._epoch = 0
+        self.vectorized = True
+        self.epoch_losses = []
+
+    # ------------------------------------------------------------------ minimize (loss.py:740-828)
+    def minimize(self, method="Adam", batch_size=100, num_epochs=1000, start_epoch=0, **kwargs):
+        if method not in self.torch_minimize_methods:
+            raise LossError(f"Minimization method `{method}` not supported.")
+        self.batch_size, self.num_epochs, self.start_epoch = batch_size, num_epochs, start_epoch
+        try:
+            self.optimizer = getattr(torch.optim, method)(self.calculator.model.parameters(), **kwargs)
+            if self.optimizer_state_path is not None:
+                self._load_optimizer_stat(self.optimizer_state_path)
+        except TypeError as e:
+            print(str(e))
+            idx = str(e).index("argument '") + 10
+            err_arg = str(e)[idx:].strip("'")
+            raise LossError(f"Argument `{err_arg}` not supported by optimizer `{method}`.")
+
+        loader = self.calculator.get_compute_arguments(batch_size)
+        dist = _dist()
+        chief = dist is None or dist.get_rank() == 0
+        self.epoch_losses = []
+        epoch = 0
+        for epoch in range(self.start_epoch, self.start_epoch + self.num_epochs):
+            self._epoch = epoch
+            if self.start_epoch != 0 and epoch == self.start_epoch:
+                epoch_loss = self._get_loss_epoch(loader)
+            else:
+                epoch_loss = 0
+                for batch in self._batches(loader):
+
+                    def closure():
+                        self.optimizer.zero_grad()
+                        loss = self._get_loss_batch(batch)
+                        loss.backward()
+                        return self._sync_gradients(loss)
+
+                    loss = self.optimizer.step(closure)
+                    epoch_loss += float(loss)
+                if chief:
+                    self.calculator.save_model(epoch)
+            self.epoch_losses.append(epoch_loss)
+            if chief:
+                print("Epoch = {:<6d}  loss = {:.10e}".format(epoch, epoch_loss))
+        epoch += 1
+        epoch_loss = self._get_loss_epoch(loader)
+        self.epoch_losses.append(epoch_loss)
+        if chief:
+            print("Epoch = {:<6d}  loss = {:.10e}".format(epoch, epoch_loss))
+            self.calculator.save_model(epoch, force_save=True)
+
+    def _batches(self, loader):
+        """Batches of samples.  On the vectorised route the DataLoader's per-sample collate
+        (numpy -> tensor for every value) is skipped: only configuration indices are needed."""
+        if self._fast_path():
+            n = len(self.calculator.fingerprints_dataset)
+            bs = self.batch_size if getattr(self, "batch_size", None) else loader.batch_size
+            fp = self.calculator.fingerprints_dataset.fp
+            for lo in range(0, n, bs):
+                yield fp[lo:min(lo + bs, n)]
+        else:
+            for batch in loader:
+                yield batch
+
+    def _get_loss_epoch(self, loader):
+        total = 0.0
+        with torch.enable_grad():
+            for batch in self._batches(loader):
+                loss = self._get_loss_batch(batch)
+                total += float(self._sync_loss(loss.detach()))
+        return total
+
+    # ------------------------------------------------------------------ data-parallel plumbing
+    def _sync_gradients(self, loss):
+        dist = _dist()
+        if dist is None:
+            return loss
+        params = [p for p in self.calculator.model.parameters() if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1) for p in params] + [loss.detach().reshape(1)])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        pos = 0
+        for p in params:
+            p.grad.copy_(flat[pos:pos + p.numel()].view_as(p.grad))
+            pos += p.numel()
+        return flat[pos]
+
+    def _sync_loss(self, loss):
+        dist = _dist()
+        if dist is None:
+            return loss
+        v = loss.detach().clone().reshape(1)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        return v[0]
+
+    def _my_share(self, batch):
+        dist = _dist()
+        if dist is None:
+            return batch
+        r, w = dist.get_rank(), dist.get_world_size()
+        n = len(batch)
+        lo, hi = (n * r) // w, (n * (r + 1)) // w
+        return batch[lo:hi]
+
+    # ------------------------------------------------------------------ batch loss (loss.py:843-877)
+    def _fast_path(self):
+        calc = self.calculator
+        return (self.vectorized and self._default_residual and getattr(calc, "_packed", None) is not None
+                and getattr(calc, "_ref", None) is not None and calc.use_energy and not calc.use_stress)
+
+    def _get_loss_batch(self, batch, normalize=True):
+        nglobal = len(batch)
+        batch = self._my_share(batch)
+        if len(batch) == 0:
+            params = list(self.calculator.model.parameters())
+            loss = sum((p * 0.0).sum() for p in params)
+        elif self._fast_path() and self.calculator._packed_usable(batch):
+            loss = self._loss_vectorized(batch)
+        else:
+            results = self.calculator.compute(batch)
+            energy_batch = results["energy"]
+            forces_batch = results["forces"] if results["forces"] is not None else [None] * len(batch)
+            stress_batch = results["stress"] if results["stress"] is not None else [None] * len(batch)
+            losses = [self._get_loss_single_config(s, e, f, st)
+                      for s, e, f, st in zip(batch, energy_batch, forces_batch, stress_batch)]
+            loss = torch.stack(losses).sum()
+        if normalize:
+            loss = loss / nglobal
+        return loss
+
+    def _loss_vectorized(self, batch):
+        """Same arithmetic as `energy_forces_residual` + sum of squares, over the whole batch."""
+        calc = self.calculator
+        idx = [s["index"] for s in batch]
+        energy, forces, natoms = calc.compute_packed(idx)
+        dev, dt = energy.device, energy.dtype
+        P, ref = calc._packed, calc._ref
+        wc = torch.as_tensor([s["configuration"].weight.config_weight for s in batch], device=dev, dtype=dt)
+        we = torch.as_tensor([s["configuration"].weight.energy_weight for s in batch], device=dev, dtype=dt)
+        nat = torch.as_tensor(natoms, device=dev, dtype=dt)
+        denom = nat if self.residual_data["normalize_by_natoms"] else torch.ones_like(nat)
+        idx_t = torch.as_tensor(idx, device=dev)
+        res_e = wc * we * (energy - ref["energy"].index_select(0, idx_t)) / denom
+        loss = (res_e * res_e).sum()
+        if calc.use_forces:
+            wf = torch.as_tensor([s["configuration"].weight.forces_weight for s in batch], device=dev, dtype=dt)
+            if _is_run(idx):
+                fref = ref["forces"][3 * int(P.cfg_ptr[idx[0]]):3 * int(P.cfg_ptr[idx[-1] + 1])]
+            else:
+                fref = torch.cat([ref["forces"][3 * int(P.cfg_ptr[i]):3 * int(P.cfg_ptr[i + 1])]
+                                  for i in idx])
+            per_comp = torch.repeat_interleave(wc * wf / denom, 3 * torch.as_tensor(natoms, device=dev))
+            res_f = per_comp * (forces - fref)
+            loss = loss + (res_f * res_f).sum()
+        return loss
+
+    def _get_loss_single_config(self, sample, pred_energy, pred_forces, pred_stress):
+        """loss.py:879-920."""
+        device = self.calculator.model.device
+        calc = self.calculator
+        if calc.use_energy:
+            pred = pred_energy.reshape(-1)
+            ref = _t(sample["energy"]).reshape(-1).to(device)
+        if calc.use_forces:
+            ref_forces = _t(sample["forces"]).to(device)
+            if calc.use_energy:
+                pred = torch.cat((pred, pred_forces.reshape(-1)))
+                ref = torch.cat((ref, ref_forces.reshape(-1)))
+            else:
+                pred, ref = pred_forces.reshape(-1), ref_forces.reshape(-1)
+        if calc.use_stress:
+            ref_stress = _t(sample["stress"]).to(device)
+            pred = torch.cat((pred, pred_stress.reshape(-1)))
+            ref = torch.cat((ref, ref_stress.reshape(-1)))
+        conf = sample["configuration"]
+        residual = self.residual_fn(conf.identifier, conf.get_num_atoms(), conf.weight, pred, ref,
+                                    self.residual_data)
+        return torch.sum(torch.pow(residual, 2))
+
+    # ------------------------------------------------------------------ optimizer state (loss.py:922-935)
+    def save_optimizer_state(self, path="optimizer_state.pkl"):
+        torch.save(self.optimizer.state_dict(), path)
+
+    def load_optimizer_state(self, path="optimizer_state.pkl"):
+        self.optimizer_state_path = path
+
+    def _load_optimizer_stat(self, path):
+        self.optimizer.load_state_dict(torch.load(path))
+
+
+def _t(x):
+    return x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x))
+
+
+def _is_run(idx):
+    return all(idx[k + 1] == idx[k] + 1 for k in range(len(idx) - 1))

@@ -20,8 +20,8 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+def _ptr(t, byte_offset=0):
+    return C.c_void_p(t.data_ptr() + byte_offset) if t is not None else C.c_void_p(0)
 
 
 def _need_cuda(*ts):
@@ -240,7 +240,8 @@ def _scatter_fwd(dEdG, pack):
     check(_lib.lib().kb_force_scatter_fwd(n_centers, _ptr(pack.get("centers")), _ptr(pack["offsets"]),
                                           _ptr(idx), _ptr(pack["image"]), pack["D"], _ptr(dEdG),
                                           _ptr(pack.get("scale")), _ptr(pack["dz"]),
-                                          _ptr(pack["dz_ptr"]), _ptr(F), _stream()),
+                                          _ptr(pack["dz_ptr"]),
+                                          _ptr(F, -24 * int(pack.get("out_base", 0))), _stream()),
           "kb_force_scatter_fwd")
     return F
 
@@ -252,7 +253,8 @@ def _scatter_bwd(gF, pack):
     out = torch.empty((n_centers, pack["D"]), dtype=torch.float64, device=gF.device)
     check(_lib.lib().kb_force_scatter_bwd(n_centers, _ptr(pack.get("centers")), _ptr(pack["offsets"]),
                                           _ptr(pack["indices"]), _ptr(pack["image"]), pack["D"],
-                                          _ptr(gF), _ptr(pack.get("scale")), _ptr(pack["dz"]),
+                                          _ptr(gF, -24 * int(pack.get("out_base", 0))),
+                                          _ptr(pack.get("scale")), _ptr(pack["dz"]),
                                           _ptr(pack["dz_ptr"]), _ptr(out), _stream()),
           "kb_force_scatter_bwd")
     return out

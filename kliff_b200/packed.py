@@ -1,0 +1,221 @@
+"""GPU-resident packed fingerprints: what the descriptor kernels produce for a list of
+configurations and what the force-scatter kernel consumes.
+
+The reference keeps, per configuration, a dense `dzetadr_forces` of shape (N, D, 3N)
+(kliff/legacy/descriptors/symmetry_function/sym_fn.py:163-174) and re-uploads it every batch
+(calculator_torch.py:211).  Here all configurations are concatenated into one atom array
+(per configuration: contributing atoms, then its padding atoms) with one CSR neighbor list, and
+the gradient stays in the kernels' native per-atom block layout [D][n+1][3]:
+
+    coords   f64 [A, 3]      all atoms of all configurations
+    code     i32 [A]         species code (cutoff-matrix index)
+    image    i32 [A]         ordinal of the contributing atom an atom is an image of
+    offsets  i64 [A + 1]     CSR over atoms (padding atoms have empty lists)
+    indices  i32 [sum n]     neighbor atom ids, ascending per atom
+    centers  i32 [Nc]        atom id of every contributing atom (configuration-major)
+    zeta     f64 [Nc, D]     raw descriptors
+    dz       f64 [...]       blocks, atom t at dz[dz_ptr[t]:], 128-byte aligned
+    cfg_ptr  host int64 [C+1]  centre range of configuration c = [cfg_ptr[c], cfg_ptr[c+1])
+
+Memory: 36 KB per atom in fp64 for set51 at n = 28.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+class PackedGradient:
+    """Host copy of one configuration's gradient blocks, picklable; stands in for the dense
+    `dzetadr_forces` array inside a fingerprints pickle (`to_dense()` gives the reference's
+    (N, D, 3N) array)."""
+
+    def __init__(self, values, counts, neighbors, image, n_desc):
+        self.values = values        # 1-D, blocks [D][n_t+1][3] back to back (already / stdev)
+        self.counts = counts        # i32 [N]
+        self.neighbors = neighbors  # i32 [sum counts], LOCAL atom ids (contributing + padding)
+        self.image = image          # i32 [N + P], local owner of every atom
+        self.n_desc = n_desc
+
+    def to_dense(self):
+        N, D = len(self.counts), self.n_desc
+        out = np.zeros((N, D, N, 3), dtype=self.values.dtype)
+        pos = nb = 0
+        for t in range(N):
+            n = int(self.counts[t])
+            blk = self.values[pos:pos + 3 * D * (n + 1)].reshape(D, n + 1, 3)
+            ids = np.concatenate((self.neighbors[nb:nb + n], [t]))
+            for slot, a in enumerate(ids):
+                out[t, :, self.image[a], :] += blk[:, slot, :]
+            pos += 3 * D * (n + 1)
+            nb += n
+        return out.reshape(N, D, 3 * N)
+
+    @property
+    def shape(self):
+        N = len(self.counts)
+        return (N, self.n_desc, 3 * N)
+
+
+class PackedFingerprints:
+    def __init__(self, D, device):
+        self.D = D
+        self.device = device
+        self.coords = self.code = self.image = self.offsets = self.indices = None
+        self.centers = self.zeta = self.dz = self.dz_ptr = None
+        self.cfg_ptr = np.zeros(1, np.int64)   # centre ranges
+        self.atom_ptr = np.zeros(1, np.int64)  # atom ranges (contributing + padding)
+        self.maxn = 0
+        self.scale = None  # 1/stdev when normalised, folded into the contraction
+
+    @property
+    def n_configs(self):
+        return len(self.cfg_ptr) - 1
+
+    @property
+    def n_centers(self):
+        return int(self.cfg_ptr[-1])
+
+    # ------------------------------------------------------------------ assembly
+    @classmethod
+    def from_parts(cls, D, device, parts):
+        """parts: per configuration dict(coords, code, image_local, counts, indices_local,
+        n_contrib) of device tensors; concatenates with index shifting."""
+        self = cls(D, device)
+        atom_base, cen_base = 0, 0
+        coords, code, image, counts, indices, centers = [], [], [], [], [], []
+        atom_ptr, cfg_ptr = [0], [0]
+        maxn = 0
+        for p in parts:
+            na = p["coords"].shape[0]
+            coords.append(p["coords"])
+            code.append(p["code"])
+            image.append(p["image_local"] + cen_base)
+            counts.append(p["counts"])
+            indices.append(p["indices_local"] + atom_base)
+            centers.append(torch.arange(atom_base, atom_base + p["n_contrib"], dtype=torch.int32,
+                                        device=device))
+            atom_base += na
+            cen_base += p["n_contrib"]
+            atom_ptr.append(atom_base)
+            cfg_ptr.append(cen_base)
+            maxn = max(maxn, p["maxn"])
+        self.coords = torch.cat(coords)
+        self.code = torch.cat(code).to(torch.int32)
+        self.image = torch.cat(image).to(torch.int32)
+        cnt = torch.cat(counts)
+        self.offsets = torch.zeros(cnt.shape[0] + 1, dtype=torch.int64, device=device)
+        torch.cumsum(cnt, 0, out=self.offsets[1:])
+        self.indices = torch.cat(indices).to(torch.int32) if indices else torch.zeros(0, dtype=torch.int32, device=device)
+        self.centers = torch.cat(centers)
+        self.atom_ptr = np.asarray(atom_ptr, np.int64)
+        self.cfg_ptr = np.asarray(cfg_ptr, np.int64)
+        self.maxn = maxn
+        return self
+
+    def compute(self, params, grad=True, mode=0):
+        """Run the descriptor kernel over every centre atom (one launch)."""
+        self.zeta, self.dz, self.dz_ptr = ops.symfun_forward(
+            params, self.coords, self.code, self.offsets, self.indices, self.maxn,
+            centers=self.centers, grad=grad, mode=mode)
+        return self
+
+    # ------------------------------------------------------------------ per-configuration views
+    def config_slice(self, c):
+        return int(self.cfg_ptr[c]), int(self.cfg_ptr[c + 1])
+
+    def counts_of(self, c):
+        lo, hi = self.config_slice(c)
+        a0 = int(self.atom_ptr[c])
+        return (self.offsets[a0 + 1:a0 + (hi - lo) + 1] - self.offsets[a0:a0 + (hi - lo)]).to(torch.int32)
+
+    def pack_for(self, lo, hi):
+        """Argument pack of the force-scatter kernels for the centre range [lo, hi) (a run of
+        whole configurations).  Forces come out relative to contributing atom `lo`."""
+        return dict(offsets=self.offsets, indices=self.indices, image=self.image, dz=self.dz,
+                    dz_ptr=self.dz_ptr[lo:hi + 1], centers=self.centers[lo:hi], D=self.D,
+                    n_out=hi - lo, out_base=lo, scale=self.scale)
+
+    def dense_config(self, c, want_forces=True, want_stress=False):
+        """The reference's dense per-configuration views (sym_fn.py:163-185)."""
+        lo, hi = self.config_slice(c)
+        a0 = int(self.atom_ptr[c])
+        pack = dict(offsets=self.offsets, indices=self.indices, dz=self.dz, dz_ptr=self.dz_ptr[lo:hi + 1],
+                    centers=self.centers[lo:hi], D=self.D,
+                    image=self.image - lo)  # owners local to the configuration
+        del a0
+        return ops.dense_fold(pack, self.coords, hi - lo, want_forces, want_stress)
+
+    def packed_gradient_host(self, c, dtype, inv_scale=None):
+        """PackedGradient (host, picklable) of configuration c, optionally divided by stdev."""
+        lo, hi = self.config_slice(c)
+        a0, a1 = int(self.atom_ptr[c]), int(self.atom_ptr[c + 1])
+        n = hi - lo
+        counts = self.counts_of(c).cpu().numpy()
+        ptr = self.dz_ptr[lo:hi + 1].cpu().numpy()
+        raw = self.dz[int(ptr[0]):int(ptr[-1])]
+        if inv_scale is not None:
+            # blocks are [D][n+1][3]: scale row d by 1/stdev[d]
+            raw = raw.clone()
+            for t in range(n):
+                s, ln = int(ptr[t] - ptr[0]), 3 * self.D * (int(counts[t]) + 1)
+                raw[s:s + ln].view(self.D, -1).mul_(inv_scale[:, None])
+        raw = raw.cpu().numpy()
+        vals = np.concatenate([raw[int(ptr[t] - ptr[0]):int(ptr[t] - ptr[0]) + 3 * self.D * (int(counts[t]) + 1)]
+                               for t in range(n)]) if n else np.zeros(0)
+        o0, o1 = int(self.offsets[a0]), int(self.offsets[a0 + n])
+        nbrs = (self.indices[o0:o1] - a0).cpu().numpy().astype(np.int32)
+        image = (self.image[a0:a1] - lo).cpu().numpy().astype(np.int32)
+        return PackedGradient(vals.astype(dtype), counts.astype(np.int32), nbrs, image, self.D)
+
+    @classmethod
+    def from_packed_gradients(cls, D, device, grads):
+        """Rebuild the device store from PackedGradient objects (fingerprints loaded from disk).
+        Coordinates are not needed for the force contraction and are left empty."""
+        self = cls(D, device)
+        atom_base = cen_base = 0
+        counts, indices, image, centers, vals, sizes = [], [], [], [], [], []
+        atom_ptr, cfg_ptr = [0], [0]
+        for g in grads:
+            N, A = len(g.counts), len(g.image)
+            full = np.zeros(A, np.int64)
+            full[:N] = g.counts
+            counts.append(full)
+            indices.append(g.neighbors.astype(np.int64) + atom_base)
+            image.append(g.image.astype(np.int64) + cen_base)
+            centers.append(np.arange(atom_base, atom_base + N))
+            vals.append(np.asarray(g.values, np.float64))
+            sizes.append(3 * D * (np.asarray(g.counts, np.int64) + 1))
+            atom_base += A
+            cen_base += N
+            atom_ptr.append(atom_base)
+            cfg_ptr.append(cen_base)
+        cnt = np.concatenate(counts)
+        off = np.zeros(len(cnt) + 1, np.int64)
+        np.cumsum(cnt, out=off[1:])
+        sz = np.concatenate(sizes)
+        padded = (sz + 15) // 16 * 16
+        ptr = np.zeros(len(sz) + 1, np.int64)
+        np.cumsum(padded, out=ptr[1:])
+        flat = np.zeros(int(ptr[-1]))
+        src = np.concatenate(vals) if vals else np.zeros(0)
+        spos = np.zeros(len(sz) + 1, np.int64)
+        np.cumsum(sz, out=spos[1:])
+        for t in range(len(sz)):
+            flat[ptr[t]:ptr[t] + sz[t]] = src[spos[t]:spos[t + 1]]
+        self.offsets = torch.as_tensor(off, device=device)
+        self.indices = torch.as_tensor(np.concatenate(indices).astype(np.int32), device=device)
+        self.image = torch.as_tensor(np.concatenate(image).astype(np.int32), device=device)
+        self.centers = torch.as_tensor(np.concatenate(centers).astype(np.int32), device=device)
+        self.dz = torch.as_tensor(flat, device=device)
+        self.dz_ptr = torch.as_tensor(ptr, device=device)
+        self.atom_ptr = np.asarray(atom_ptr, np.int64)
+        self.cfg_ptr = np.asarray(cfg_ptr, np.int64)
+        self.maxn = int(cnt.max()) if len(cnt) else 0
+        return self
+
+    # ------------------------------------------------------------------ force contraction
+    def forces(self, dEdG, lo, hi):
+        """Flat forces f64 [3*(hi-lo)] of the contributing atoms [lo, hi), differentiable w.r.t.
+        dEdG (shape [hi-lo, D]): F = -sum dEdG * scale * dG/dr."""
+        return ops.force_scatter(dEdG, self.pack_for(lo, hi))

@@ -1,0 +1,275 @@
+"""The reference's own hot-path tests, re-stated against the drop-in plugin API
+(kliff_b200.neighbor / legacy.descriptors / legacy.calculators / legacy.loss):
+tests/test_neighbor.py, tests/descriptors/test_symmetry_function.py, tests/descriptors/
+test_descriptor.py, tests/calculators/test_calculator_torch.py, tests/test_dunn_optimize.py and
+the two published tutorial loss sequences."""
+import json
+import os
+import pickle
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, fams_from_npz, load_golden
+from helpers import config_from_golden, configs_from_npz
+from kliff_b200.dataset import Configuration
+from kliff_b200.dataset.weight import Weight
+from kliff_b200.legacy import nn
+from kliff_b200.legacy.calculators import CalculatorTorch, CalculatorTorchSeparateSpecies
+from kliff_b200.legacy.descriptors import SymmetryFunction, load_fingerprints
+from kliff_b200.legacy.loss import Loss
+from kliff_b200.models import NeuralNetwork
+from kliff_b200.neighbor import NeighborList, NeighborListError, assemble_forces
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def workdir(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    return tmp_path
+
+
+# ------------------------------------------------------------------------------ neighbor
+def test_neighbor_list_api():
+    g = load_golden("ref_kat_neighbor.npz")
+    conf = config_from_golden(g, symbols=["O", "C", "C", "C"])
+    neigh = NeighborList(conf, infl_dist=2, padding_need_neigh=False)
+    target_species = ["C"] * 16
+    for i in (0, 10, 12, 14):
+        target_species[i] = "O"
+    assert np.allclose(neigh.get_coords(), g["target_coords"])
+    assert np.array_equal(neigh.get_species(), target_species)
+    for i in range(4):
+        idx, xyz, sp = neigh.get_neigh(i)
+        assert np.array_equal(np.sort(idx), np.sort(g["all_indices"][i]))
+        assert np.allclose(xyz, g["target_coords"][idx])
+        assert list(sp) == [target_species[j] for j in idx]
+    for i in range(4, 16):
+        idx, xyz, sp = neigh.get_neigh(i)
+        assert idx.size == 0 and xyz.size == 0 and sp.size == 0
+    numneigh, neighlist = neigh.get_numneigh_and_neighlist_1D(request_padding=False)
+    assert np.array_equal(numneigh, [3, 3, 3, 3])
+    assert np.array_equal(neighlist, np.concatenate([np.sort(r) for r in g["all_indices"]]))
+    with pytest.raises(NeighborListError):
+        neigh.get_numneigh_and_neighlist_1D(request_padding=True)
+    assert np.array_equal(neigh.get_image()[:4], np.arange(4))
+    assert neigh.get_padding_image().shape == (12,)
+    # image fold of forces (neighbor.py:260-296)
+    f = np.arange(48, dtype=float).reshape(16, 3)
+    tot = assemble_forces(f, 4, neigh.padding_image)
+    ref = f[:4].copy()
+    for p, owner in enumerate(neigh.padding_image):
+        ref[owner] += f[4 + p]
+    assert np.allclose(tot, ref)
+
+
+def test_neighbor_list_errors():
+    conf = Configuration(cell=np.eye(3) * 10, species=["Si", "Si"],
+                         coords=np.array([[0.0, 0, 0], [1e-7, 0, 0]]), PBC=[True] * 3)
+    with pytest.raises(NeighborListError):
+        NeighborList(conf, 3.0)
+    conf = Configuration(cell=np.zeros((3, 3)), species=["Si"], coords=np.zeros((1, 3)), PBC=[True] * 3)
+    with pytest.raises(NeighborListError):
+        NeighborList(conf, 3.0)
+
+
+# ------------------------------------------------------------------------------ descriptor
+def kat_descriptor():
+    p = OrderedDict()
+    p["g1"] = None
+    p["g2"] = [{"eta": 0.0009, "Rs": 0.0}, {"eta": 0.01, "Rs": 0.0}]
+    p["g3"] = [{"kappa": 0.03214}, {"kappa": 0.13123}]
+    p["g4"] = [{"zeta": 1, "lambda": -1, "eta": 0.0001}, {"zeta": 2, "lambda": 1, "eta": 0.003}]
+    p["g5"] = [{"zeta": 1, "lambda": -1, "eta": 0.0001}, {"zeta": 2, "lambda": 1, "eta": 0.003}]
+    return SymmetryFunction({"Si-Si": 4.5}, "cos", p)  # positional, as the reference test does
+
+
+def test_symmetry_function_transform_kat():
+    """tests/descriptors/test_symmetry_function.py:294-307."""
+    g = load_golden("ref_kat_symfun.npz")
+    conf = config_from_golden(g)
+    desc = kat_descriptor()
+    assert len(desc) == 9 and desc.get_size() == 9
+    for fit_forces in (False, True):
+        for fit_stress in (False, True):
+            zeta, dzf, dzs = desc.transform(conf, fit_forces, fit_stress)
+            assert np.allclose(zeta, g["zeta_ref"])
+            assert (dzf is not None) == fit_forces and (dzs is not None) == fit_stress
+            if fit_forces:
+                assert dzf.shape == (8, 9, 24)
+                assert np.allclose(dzf[0], g["dzetadr_forces_ref"])
+            if fit_stress:
+                assert np.allclose(dzs[0], g["dzetadr_stress_ref"])
+
+
+def test_contraction_with_ones_property():
+    """tests/transformations/test_descriptors.py:14-72 (property half): tensordot(ones, dzetadr)
+    equals the VJP with ones; here: dense view vs force-scatter kernel."""
+    confs = configs_from_npz("si_varying_alat.npz", limit=1)
+    for hp, D in (("set30", 30), ("set51", 51)):
+        desc = SymmetryFunction({"Si-Si": 4.5}, "cos", hp)
+        zeta, dzf, _ = desc.transform(confs[0], fit_forces=True)
+        n = confs[0].get_num_atoms()
+        assert zeta.shape == (n, D) and dzf.shape == (n, D, 3 * n)
+        dense = np.tensordot(np.ones((n, D)), dzf, ([0, 1], [0, 1]))
+        packed = desc.transform_packed([confs[0]])
+        F = packed.forces(torch.ones((n, D), dtype=torch.float64, device=packed.device), 0, n)
+        assert np.allclose(-F.cpu().numpy(), dense, rtol=1e-10, atol=1e-10 * np.abs(dense).max())
+
+
+def test_generate_fingerprints_normalisation(workdir):
+    """tests/descriptors/test_descriptor.py:81-145: mean/stdev (np.mean/np.std), normalised zeta and
+    dzetadr in the pickle, state file; both gradient formats."""
+    confs = configs_from_npz("si_varying_alat.npz", limit=3) + configs_from_npz("si_varying_alat.npz")[-2:]
+    raw = SymmetryFunction({"Si-Si": 5.0}, "cos", "set30", normalize=False, dtype=np.float64)
+    zs = [raw.transform(c, fit_forces=True) for c in confs]
+    stacked = np.concatenate([z[0] for z in zs])
+    mean, stdev = np.mean(stacked, axis=0), np.std(stacked, axis=0)
+    for fmt in ("packed", "dense"):
+        desc = SymmetryFunction({"Si-Si": 5.0}, "cos", "set30", normalize=True, dtype=np.float64)
+        desc.fingerprints_format = fmt
+        path = desc.generate_fingerprints(confs, fit_forces=True, fingerprints_filename=f"fp_{fmt}.pkl",
+                                          fingerprints_mean_stdev_filename=f"ms_{fmt}.pkl",
+                                          use_welford_method=(fmt == "dense"), nprocs=2)
+        assert np.allclose(desc.mean, mean, rtol=1e-12) and np.allclose(desc.stdev, stdev, rtol=1e-10)
+        state = pickle.load(open(f"ms_{fmt}.pkl", "rb"))
+        assert set(state) == {"mean", "stdev", "size"} and state["size"] == 30
+        data = load_fingerprints(path)
+        assert len(data) == len(confs)
+        for (z, dz, _), ex, c in zip(zs, data, confs):
+            assert set(ex) >= {"configuration", "zeta", "energy", "dzetadr_forces", "forces"}
+            assert np.allclose(ex["zeta"], (z - mean) / stdev, rtol=1e-9, atol=1e-9)
+            dense = ex["dzetadr_forces"] if fmt == "dense" else ex["dzetadr_forces"].to_dense()
+            ref = dz / np.atleast_3d(stdev)
+            assert np.allclose(dense, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+            assert np.allclose(ex["forces"], c.forces) and np.isclose(ex["energy"], c.energy)
+    # no normalisation: mean/stdev stay None, no state file is written
+    path = raw.generate_fingerprints(confs[:2], fit_forces=False, fingerprints_filename="fp_raw.pkl")
+    assert raw.mean is None and not os.path.exists("fingerprints_mean_and_stdev.pkl")
+    assert "dzetadr_forces" not in load_fingerprints(path)[0]
+
+
+# ------------------------------------------------------------------------------ calculator
+def make_model(desc, n1=10, n2=10):
+    model = NeuralNetwork(desc)
+    model.add_layers(nn.Linear(desc.get_size(), n1), nn.Tanh(), nn.Linear(n1, n2), nn.Tanh(),
+                     nn.Linear(n2, 1))
+    return model
+
+
+def test_calculator_torch_parameters_and_forces(workdir):
+    """tests/calculators/test_calculator_torch.py:95-162."""
+    confs = configs_from_npz("si_varying_alat.npz", limit=4)
+    desc = SymmetryFunction({"Si-Si": 5.0}, "cos", "set30", normalize=True)
+    model = make_model(desc)
+    calc = CalculatorTorch(model, gpu=False)
+    calc.create(confs, nprocs=1)
+    sizes, nelems, nparams = calc.get_size_opt_params()
+    assert [tuple(s) for s in sizes] == [(10, 30), (10,), (10, 10), (10,), (1, 10), (1,)]
+    assert nparams == 431 and calc.get_num_opt_params() == 431
+    loader = calc.get_compute_arguments(batch_size=4)
+    batch = next(iter(loader))
+    calc.update_model_params(np.zeros(nparams))
+    assert np.allclose(calc.get_opt_params(), 0.0)
+    out = calc.compute(batch)
+    assert all(float(e) == 0.0 for e in out["energy"])
+    assert all(torch.count_nonzero(f) == 0 for f in out["forces"])
+    calc.update_model_params(np.ones(nparams))
+    assert np.allclose(calc.get_opt_params(), 1.0)
+    out = calc.compute(batch)
+    assert all(f.shape == (192,) and torch.count_nonzero(f) > 0 for f in out["forces"])
+    # the packed kernel path agrees with the reference's dense tensordot formulation
+    dense = CalculatorTorch(make_model(SymmetryFunction({"Si-Si": 5.0}, "cos", "set30", normalize=True)))
+    dense.model.descriptor.fingerprints_format = "dense"
+    dense.create(confs, fingerprints_filename="fp_dense.pkl", fingerprints_mean_stdev_filename="ms_dense.pkl")
+    dense._packed = None
+    dense.update_model_params(np.ones(nparams))
+    out_d = dense.compute(next(iter(dense.get_compute_arguments(batch_size=4))))
+    for a, b in zip(out["forces"], out_d["forces"]):
+        assert torch.allclose(a, b, rtol=2e-4, atol=2e-4 * float(b.abs().max()))
+    for a, b in zip(out["energy"], out_d["energy"]):
+        assert torch.allclose(a, b, rtol=1e-5)
+
+
+def test_calculator_reuse_fingerprints(workdir):
+    confs = configs_from_npz("si_varying_alat.npz", limit=3)
+    calc = CalculatorTorch(make_model(SymmetryFunction({"Si-Si": 5.0}, "cos", "set51", normalize=True)))
+    calc.create(confs, fingerprints_filename="fp.pkl", fingerprints_mean_stdev_filename="ms.pkl")
+    ref = calc.compute(next(iter(calc.get_compute_arguments(3))))
+    calc2 = CalculatorTorch(make_model(SymmetryFunction({"Si-Si": 5.0}, "cos", "set51", normalize=True)))
+    calc2.create(confs, fingerprints_filename="fp.pkl", fingerprints_mean_stdev_filename="ms.pkl", reuse=True)
+    assert np.allclose(calc2.model.descriptor.mean, calc.model.descriptor.mean)
+    out = calc2.compute(next(iter(calc2.get_compute_arguments(3))))
+    for a, b in zip(ref["forces"], out["forces"]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(a.abs().max()))
+    from kliff_b200.legacy.calculators import CalculatorTorchError
+    with pytest.raises(CalculatorTorchError):
+        calc2.create(confs, fingerprints_filename="missing.pkl", reuse=True)
+
+
+# ------------------------------------------------------------------------------ training
+LOSSES = json.load(open(os.path.join(GOLDEN, "published_losses.json")))
+
+
+def test_published_loss_sequence_si(workdir, capsys):
+    """docs/source/tutorials/nn_Si.rst:173-183 (= README example with Weight(forces_weight=0.3)):
+    fp32, seed 35, Adam lr 1e-3, batch 100, 10 epochs + final pass.  Tolerance 1e-4 relative:
+    the reference contracts in fp32 on the CPU, this path in fp64 on the GPU."""
+    weight = Weight(forces_weight=0.3)
+    confs = configs_from_npz("si_varying_alat.npz", weight=weight)
+    desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": 5.0}, hyperparams="set51", normalize=True)
+    model = make_model(desc)
+    calc = CalculatorTorch(model, gpu=False)
+    calc.create(confs)
+    loss = Loss(calc)
+    loss.minimize(method="Adam", num_epochs=10, batch_size=100, lr=0.001)
+    ref = np.array(LOSSES["nn_Si.rst:173-183"])
+    got = np.array(loss.epoch_losses)
+    print("si rel err", np.abs(got / ref - 1).max())
+    assert np.allclose(got, ref, rtol=1e-4)
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("Epoch")]
+    assert len(lines) == 11 and lines[0].startswith("Epoch = 0       loss = 7.33")
+    assert os.path.exists("kliff_saved_model/model_epoch10.pkl")
+    # the reference's per-configuration route gives the same loss as the vectorised one
+    loss2 = Loss(calc)
+    loss2.vectorized = False
+    loader = calc.get_compute_arguments(100)
+    a = loss._get_loss_epoch(loader)
+    b = loss2._get_loss_epoch(loader)
+    assert abs(a - b) <= 1e-5 * abs(a)
+
+
+def test_published_loss_sequence_sic(workdir):
+    """docs/source/tutorials/nn_SiC.rst:104-114: two species, one MLP each, batch 4."""
+    weight = Weight(forces_weight=0.3)
+    confs = configs_from_npz("sic_training_set.npz", weight=weight)
+    desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": 5.0, "C-C": 5.0, "Si-C": 5.0},
+                            hyperparams="set51", normalize=True)
+    model_si = make_model(desc)
+    model_si.set_save_metadata(prefix="./kliff_saved_model_si", start=5, frequency=2)
+    model_c = make_model(desc)
+    model_c.set_save_metadata(prefix="./kliff_saved_model_c", start=5, frequency=2)
+    calc = CalculatorTorchSeparateSpecies({"Si": model_si, "C": model_c}, gpu=False)
+    calc.create(confs, reuse=False)
+    loss = Loss(calc)
+    loss.minimize(method="Adam", num_epochs=10, batch_size=4, lr=0.001)
+    ref = np.array(LOSSES["nn_SiC.rst:104-114"])
+    got = np.array(loss.epoch_losses)
+    print("sic rel err", np.abs(got / ref - 1).max())
+    assert np.allclose(got, ref, rtol=1e-4)
+    assert os.path.exists("kliff_saved_model_si/model_Si_epoch7.pkl")
+
+
+def test_custom_residual_function_route(workdir):
+    """A user residual_fn forces the reference's per-configuration loop (loss.py:867-920)."""
+    from kliff_b200.legacy.loss import energy_residual
+    confs = configs_from_npz("si_varying_alat.npz", limit=6)
+    calc = CalculatorTorch(make_model(SymmetryFunction({"Si-Si": 5.0}, "cos", "set30", normalize=True)))
+    calc.create(confs, use_forces=False)
+    loss = Loss(calc, residual_fn=energy_residual, residual_data={"normalize_by_natoms": False})
+    loss.minimize(method="Adam", num_epochs=3, batch_size=2, lr=0.01)
+    assert len(loss.epoch_losses) == 4 and loss.epoch_losses[-1] < loss.epoch_losses[0]
