@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (contract: see the task statement / DESIGN.md §5).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's C++ on host cores
+
+Workload (BASELINE.json configs[1]): synthetic jittered diamond-Si supercell, nx^3 conventional
+cells (default 50 -> 1 000 000 atoms), a = 5.431 A, sigma = 0.05 A, set51, cos cutoff 5.0 A, fp64.
+One step = one pass of the hot path over that supercell: padding atoms -> cell-list neighbor
+list -> symmetry functions + dG/dr (packed, materialised in HBM).
+metric = descriptor+dG/dr atoms/sec.  For N > 1 every rank runs the pass on its own supercell
+(weak scaling, no data-path collective); timing is per-step CUDA events, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+A_SI, SIGMA, RC = 5.431, 0.05, 5.0
+FLOP_CANON = 380618.0   # per atom, set51 / n=28 / T=378 / T4=168
+BYTES_CANON = 36724.0   # per atom, fp64 zeta + dG/dr written + inputs read once
+
+
+def diamond(nx, seed):
+    basis = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0],
+                      [.25, .25, .25], [.25, .75, .75], [.75, .25, .75], [.75, .75, .25]])
+    g = np.stack(np.meshgrid(np.arange(nx), np.arange(nx), np.arange(nx), indexing="ij"), -1).reshape(-1, 3)
+    pos = (g[:, None, :] + basis[None]).reshape(-1, 3) * A_SI
+    pos += np.random.default_rng(seed).normal(0.0, SIGMA, pos.shape)
+    return np.eye(3) * A_SI * nx, np.ascontiguousarray(pos)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 7] or \
+               [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own C++ (oracle/_ref) — or the C port when it is absent — on the
+# host cores: serial paddings + neighbor list, then generate_one_atom(grad=True) over forked workers
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _worker_init(kind, rc, kinds, rows, vals, coords, species, offsets, indices):
+    from oracle import oracle as orc
+    _W["o"] = orc.Oracle(kind)
+    fams, pos = [], 0
+    ncols = {1: 1, 2: 2, 3: 1, 4: 3, 5: 3}
+    for k, r in zip(kinds, rows):
+        c = ncols[int(k)]
+        fams.append((int(k), np.ascontiguousarray(vals[pos:pos + r * c].reshape(r, c))))
+        pos += r * c
+    _W.update(rc=rc, fams=fams, coords=coords, species=species, offsets=offsets, indices=indices)
+
+
+def _worker_run(span):
+    lo, hi = span
+    z, _ = _W["o"].symfun_range(_W["rc"], _W["fams"], lo, hi, _W["coords"], _W["species"],
+                                _W["offsets"], _W["indices"], grad=True, keep_grad=False)
+    return float(z.sum())
+
+
+class CpuBaseline:
+    def __init__(self, nx=12, cores=None):
+        import multiprocessing as mp
+        from kliff_b200.legacy.descriptors.hyperparams import get_set51
+        from oracle import oracle as orc
+        self.kind = "reference" if orc.have_reference() else "port"
+        self.cores = cores or len(os.sched_getaffinity(0))
+        o = orc.Oracle(self.kind)
+        cell, pos = diamond(nx, 0)
+        n = len(pos)
+        z = np.full(n, 14, np.int32)
+        t0 = time.time()
+        pc, ps, pi = o.create_paddings(RC, cell, [1, 1, 1], pos, z)
+        allc = np.concatenate([pos, pc])
+        need = np.zeros(len(allc), np.int32)
+        need[:n] = 1
+        counts, offsets, indices = o.build_neighbors(allc, RC, need)
+        self.t_neigh = time.time() - t0
+        self.n = n
+        fams = orc.fams_from_hyperparams(get_set51())
+        kinds = np.array([k for k, _ in fams], np.int32)
+        rows = np.array([v.shape[0] for _, v in fams], np.int32)
+        vals = np.concatenate([v.reshape(-1) for _, v in fams])
+        ctx = mp.get_context("fork")
+        self.pool = ctx.Pool(self.cores, initializer=_worker_init,
+                             initargs=(self.kind, np.array([[RC]]), kinds, rows, vals, allc,
+                                       np.zeros(len(allc), np.int32), offsets, indices))
+
+    def run(self, natoms):
+        """Descriptor + dG/dr of `natoms` atoms (cyclic over the sample cell) on all cores.
+        Returns atoms/s."""
+        chunk = max(8, min(256, natoms // (self.cores * 4) or 8))
+        spans, done = [], 0
+        while done < natoms:
+            lo = done % self.n
+            hi = min(lo + chunk, self.n, lo + (natoms - done))
+            spans.append((lo, hi))
+            done += hi - lo
+        t0 = time.time()
+        self.pool.map(_worker_run, spans)
+        return natoms / (time.time() - t0)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's C++ descriptor path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    base = CpuBaseline(nx=12)
+    per_core = 470.0  # atoms/s/core measured for the reference in the build container
+    sample = int(max(2000, min(200000, per_core * base.cores * 4.0)))  # ~4 s per step
+    for _ in range(max(1, min(args.warmup, 1))):
+        base.run(max(base.cores * 8, sample // 8))
+    rates, t0 = [], time.time()
+    for _ in range(args.steps):
+        rates.append(base.run(sample))
+    wall = time.time() - t0
+    base.close()
+    value = sample * args.steps / wall
+    natoms_job = 8 * args.nx ** 3
+    line = {
+        "impl": "reference", "metric": "descriptor+dG/dr atoms/sec", "value": value, "unit": "atoms/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"diamond-Si {natoms_job}-atom supercell, set51, cos 5.0 A, neighbor list + "
+                               "descriptor + dG/dr (configs[1])", "nx": args.nx},
+        "cpu_baseline": {"value": value, "unit": "atoms/s", "cores": base.cores, "kind": base.kind,
+                         "sample": f"{sample} atoms per step of a {base.n}-atom jittered diamond cell "
+                                   f"(same lattice/cutoff/set51 as the job), generate_one_atom(grad=True) over "
+                                   f"{base.cores} forked workers; serial paddings+neighbor list "
+                                   f"{base.t_neigh:.2f} s not included"},
+        "e2e": {"value": value, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=50, help="conventional cells per edge (50 -> 1M atoms)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from kliff_b200 import ops
+    from kliff_b200.dataset import Configuration
+    from kliff_b200.legacy.descriptors import SymmetryFunction
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: kliff_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.device_info()  # raises unless sm_100
+
+    # ---- synthetic input, resident in HBM before the timed region
+    cell, pos = diamond(args.nx, seed=rank)
+    n = len(pos)
+    coords = torch.tensor(pos, device=dev)
+    z = torch.full((n,), 14, dtype=torch.int32, device=dev)
+    desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": RC}, hyperparams="set51", normalize=True,
+                            dtype=np.float64)
+    P = desc._params
+    D = P.n_desc
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    state = {}
+
+    def step(timers=None):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timers is not None else None
+        if ev:
+            ev[0].record()
+        pc, ps, pi = ops.create_paddings(RC, cell, [1, 1, 1], coords, z)
+        allc = torch.cat([coords, pc])
+        counts, offsets, indices, maxn = ops.build_neighbors(allc, n, RC)
+        if ev:
+            ev[1].record()
+        code = torch.zeros(allc.shape[0], dtype=torch.int32, device=dev)
+        if "dz" not in state:  # 36 GB output buffer allocated once and reused
+            dz_ptr, total = ops.block_offsets(n, None, offsets, D)
+            state.update(dz=torch.empty(total, dtype=torch.float64, device=dev), total=total)
+        dz_ptr, total = ops.block_offsets(n, None, offsets, D)
+        assert total == state["total"]
+        if ev:
+            ev[2].record()
+        zeta, dz, _ = ops.symfun_forward(P, allc, code, offsets, indices, maxn, n_centers=n,
+                                         dz_ptr=dz_ptr, dz=state["dz"])
+        if ev:
+            ev[3].record()
+            timers.append(ev)
+        state.update(zeta=zeta, offsets=offsets, indices=indices, pi=pi, dz_ptr=dz_ptr, npad=pc.shape[0],
+                     pairs=indices.numel())
+        return zeta
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+        flush.fill_(1)
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ops.launch_count()
+    timers, t_wall0 = [], time.time()
+    for _ in range(args.steps):
+        flush.fill_(0)            # L2 flush between timed steps (outside the step's events)
+        torch.cuda.synchronize()
+        step(timers)
+    barrier()
+    t_wall1 = time.time()
+    launches = ops.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    step_ms = [ev[0].elapsed_time(ev[3]) for ev in timers]
+    sym_ms = [ev[2].elapsed_time(ev[3]) for ev in timers]
+    nl_ms = [ev[0].elapsed_time(ev[1]) for ev in timers]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    value = world * n * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the plugin API: host buffers in, zeta + forces out (rank-local)
+    host_pos = torch.from_numpy(pos).pin_memory()
+    conf = Configuration(cell=cell, species=np.full(n, "Si"), coords=host_pos.numpy(), PBC=[True] * 3)
+    w = torch.randn(n, D, dtype=torch.float64, device=dev)
+    zeta_host = torch.empty((n, D), dtype=torch.float64).pin_memory()
+    f_host = torch.empty(3 * n, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        packed = desc.transform_packed([conf], grad=True, device=dev)
+        F = packed.forces(w, 0, n)
+        zeta_host.copy_(packed.zeta, non_blocking=True)
+        f_host.copy_(F, non_blocking=True)
+        torch.cuda.synchronize()
+        return packed
+
+    npad, pairs = int(state["npad"]), int(state["pairs"])
+    state.clear()
+    del timers
+    torch.cuda.empty_cache()
+    e2e_step()
+    barrier()
+    t0 = time.time()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.time() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(e2e_s)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = measured_peaks()
+    fp64_peak = ops.probe_fp64_peak()
+    sym_s = float(np.mean(sym_ms)) * 1e-3
+    ach_gbs = BYTES_CANON * n / sym_s / 1e9
+    ach_tf = FLOP_CANON * n / sym_s / 1e12
+    line = {
+        "metric": "descriptor+dG/dr atoms/sec", "value": value, "unit": "atoms/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"diamond-Si {n}-atom supercell per GPU (jitter 0.05 A, seed=rank), set51, cos 5.0 A: "
+                               "paddings + cell-list neighbor list + descriptor + dG/dr (configs[1])",
+                   "nx": args.nx, "atoms_per_gpu": n, "paddings": npad, "neighbor_pairs": pairs,
+                   "l2": "256 MiB write between timed steps (outside the step's CUDA events)",
+                   "step_breakdown_ms": {"paddings+neighbors": float(np.mean(nl_ms)),
+                                         "symfun+dG/dr": float(np.mean(sym_ms))}},
+        "roofline": {"kernel": "symfun_tiled_kernel<1,true>", "bound": "hbm", "achieved": ach_gbs,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
+                     "peak_source": peak_src,
+                     "note": "algorithmic bytes 36 724 B/atom; the kernel is FP64-pipe bound, see roofline_fp64"},
+        "roofline_fp64": {"kernel": "symfun_tiled_kernel<1,true>", "bound": "fp64", "achieved": ach_tf,
+                          "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                          "peak_source": "DFMA-chain probe in this run (kb_probe_fp64_peak)",
+                          "note": "canonical 380 618 flop/atom (SURVEY.md §8d)"},
+        "e2e": {"value": e2e_value, "unit": "atoms/s", "h2d_bytes_per_step": int(24 * n),
+                "d2h_bytes_per_step": int(8 * n * D + 24 * n),
+                "what": "SymmetryFunction.transform_packed(Configuration with pinned host coords) + "
+                        "force contraction; zeta and forces copied back to pinned host memory"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        try:
+            base = CpuBaseline(nx=12)
+            sample = int(max(2000, min(200000, 470.0 * base.cores * 12.0)))
+            base.run(base.cores * 8)
+            rate = base.run(sample)
+            base.close()
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "atoms/s", "cores": base.cores, "kind": base.kind,
+                "sample": f"{sample} atoms of a {base.n}-atom jittered diamond cell (same lattice, cutoff, "
+                          f"set51), reference generate_one_atom(grad=True) over {base.cores} forked workers"}
+        except Exception as e:  # the baseline is reported, never required
+            line["cpu_baseline"] = {"value": None, "unit": "atoms/s", "cores": 0, "kind": "port",
+                                    "sample": f"failed: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

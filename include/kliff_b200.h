@@ -26,7 +26,8 @@
  *   - return value: 0 = ok; 1 = the reference's own error class for that call (singular cell,
  *     atom collision / cell grid too large — what neighbor_list_bind.cpp:68-72,205-209 turn into
  *     RuntimeError); other positive codes are KB_ERR_*; negative = -(cudaError_t).
- *   - no global mutable state: every function may be called from any host thread; one CUDA
+ *   - no global mutable state apart from a relaxed-atomic launch counter (kb_launch_count):
+ *     every function may be called from any host thread; one CUDA
  *     context (device) per process/rank is assumed.
  */
 #ifndef KLIFF_B200_H_
@@ -185,6 +186,8 @@ int kb_dense_fold(int32_t n_centers, const int32_t* d_centers, const int64_t* d_
 /* ------------------------------------------------------------------------------------------ */
 int kb_probe_fp64_peak(double* h_tflops, void* stream);
 int kb_probe_hbm_copy(size_t bytes, double* h_gbs, void* stream);
+/* Number of kernels this library has launched in this process (reset != 0 zeroes it). */
+int64_t kb_launch_count(int32_t reset);
 
 #ifdef __cplusplus
 }

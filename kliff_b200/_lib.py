@@ -47,7 +47,7 @@ EXPORTS = [
     "kb_nl_begin", "kb_nl_finish", "kb_nl_destroy",
     "kb_symfun_block_offsets", "kb_symfun_forward",
     "kb_force_scatter_fwd", "kb_force_scatter_bwd", "kb_dense_fold",
-    "kb_probe_fp64_peak", "kb_probe_hbm_copy",
+    "kb_probe_fp64_peak", "kb_probe_hbm_copy", "kb_launch_count",
 ]
 
 _lib = None
@@ -95,10 +95,10 @@ def lib():
     L.kb_dense_fold.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.kb_probe_fp64_peak.argtypes = [C.POINTER(dbl), vp]
     L.kb_probe_hbm_copy.argtypes = [C.c_size_t, C.POINTER(dbl), vp]
+    L.kb_launch_count.argtypes = [i32]
+    L.kb_launch_count.restype = i64
     for name in EXPORTS:
-        fn = getattr(L, name)
-        if fn.restype is C.c_int:  # default
-            fn.restype = C.c_int
+        getattr(L, name)  # raises AttributeError when a declared symbol is missing
     _lib = L
     return L
 

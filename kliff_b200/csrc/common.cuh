@@ -15,10 +15,14 @@
     if (e_ != cudaSuccess) return -(int) e_;                                   \
   } while (0)
 
+// process-wide count of kernels launched by this library (bench.py reports it as gpu_launches)
+void kb_note_launch(int n = 1);
+
 #define KB_LAUNCH_CHECK()                                                      \
   do {                                                                         \
     cudaError_t e_ = cudaGetLastError();                                       \
     if (e_ != cudaSuccess) return -(int) e_;                                   \
+    kb_note_launch();                                                          \
   } while (0)
 
 static inline cudaStream_t kb_stream(void* s) { return static_cast<cudaStream_t>(s); }

@@ -1,6 +1,16 @@
 // Version / error strings / device info and the two measurement probes used by bench.py.
 #include "common.cuh"
 
+#include <atomic>
+
+static std::atomic<long long> g_launches{0};
+void kb_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" int64_t kb_launch_count(int32_t reset)
+{
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
 namespace {
 
 // 8 independent DFMA chains per thread, fully unrolled: measures the FP64 FMA pipe, not memory.
@@ -81,6 +91,7 @@ extern "C" int kb_probe_fp64_peak(double* h_tflops, void* stream)
   {
     KB_CUDA(cudaEventRecord(e0, st));
     dfma_probe_kernel<<<blocks, 256, 0, st>>>(iters, 1.0 + rep, sink);
+    kb_note_launch();
     KB_CUDA(cudaEventRecord(e1, st));
     KB_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -113,6 +124,7 @@ extern "C" int kb_probe_hbm_copy(size_t bytes, double* h_gbs, void* stream)
   {
     KB_CUDA(cudaEventRecord(e0, st));
     copy_probe_kernel<<<148 * 16, 256, 0, st>>>(a, b, n);
+    kb_note_launch();
     KB_CUDA(cudaEventRecord(e1, st));
     KB_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;

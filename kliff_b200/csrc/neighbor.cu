@@ -294,7 +294,7 @@ extern "C" int kb_nl_begin(int32_t ntot, int32_t n_need, const double* d_coords,
     double h_part[6 * 296 + 3];
     NL_TRY(cudaMallocAsync((void**) &d_part, sizeof(double) * (6 * nblk_bbox + 3), st));
     bbox_kernel<<<nblk_bbox, NL_THREADS, 0, st>>>(ntot, d_coords, d_part);
-    NL_TRY(cudaGetLastError());
+    NL_TRY(cudaGetLastError()); kb_note_launch();
     NL_TRY(cudaMemcpyAsync(d_part + 6 * nblk_bbox, d_coords, sizeof(double) * 3, cudaMemcpyDeviceToDevice, st));
     NL_TRY(cudaMemcpyAsync(h_part, d_part, sizeof(double) * (6 * nblk_bbox + 3), cudaMemcpyDeviceToHost, st));
     NL_TRY(cudaStreamSynchronize(st));
@@ -340,21 +340,21 @@ extern "C" int kb_nl_begin(int32_t ntot, int32_t n_need, const double* d_coords,
     NL_TRY(cudaMemsetAsync(d_hist, 0, sizeof(int32_t) * (size_t) ncell, st));
     NL_TRY(cudaMemsetAsync(p->d_err, 0, sizeof(int32_t) * 2, st));
     bin_hist_kernel<<<nblk, NL_THREADS, 0, st>>>(ntot, d_coords, g, d_bin, d_hist);
-    NL_TRY(cudaGetLastError());
+    NL_TRY(cudaGetLastError()); kb_note_launch();
     rc = kb_exclusive_scan<int32_t, int32_t>(d_hist, p->d_cellstart, ncell, p->d_cellstart + ncell, st);
     if (rc) goto fail;
     NL_TRY(cudaMemsetAsync(d_hist, 0, sizeof(int32_t) * (size_t) ncell, st));
     cell_fill_kernel<<<nblk, NL_THREADS, 0, st>>>(ntot, d_coords, d_bin, p->d_cellstart, d_hist,
                                                   p->d_sorted_id, p->d_sorted_xyz);
-    NL_TRY(cudaGetLastError());
+    NL_TRY(cudaGetLastError()); kb_note_launch();
     nl_count_kernel<<<nblk, NL_THREADS, 0, st>>>(ntot, n_need, d_need, half, g, p->cutsq,
                                                  p->d_cellstart, p->d_sorted_id, p->d_sorted_xyz,
                                                  d_counts, p->d_err);
-    NL_TRY(cudaGetLastError());
+    NL_TRY(cudaGetLastError()); kb_note_launch();
     rc = kb_exclusive_scan<int32_t, int64_t>(d_counts, d_offsets, ntot, d_offsets + ntot, st);
     if (rc) goto fail;
     max_count_kernel<<<296, 256, 0, st>>>(ntot, d_counts, p->d_err + 1);
-    NL_TRY(cudaGetLastError());
+    NL_TRY(cudaGetLastError()); kb_note_launch();
     NL_TRY(cudaMemcpyAsync(&p->total, d_offsets + ntot, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     NL_TRY(cudaMemcpyAsync(h_tail, p->d_err, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, st));
     NL_TRY(cudaFreeAsync(d_part, st)); d_part = nullptr;
@@ -395,6 +395,7 @@ extern "C" int kb_nl_finish(kb_nl_plan* p, int32_t* d_indices, void* stream)
                                                        p->d_sorted_xyz, p->d_offsets, d_indices);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) rc = -(int) e;
+      else kb_note_launch();
     }
   }
   kb_nl_destroy(p, stream);

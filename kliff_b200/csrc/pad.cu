@@ -308,14 +308,14 @@ extern "C" int kb_pad_begin(int32_t natoms, double cutoff, const double* h_cell,
   {
     PadGeom g = geom_of(p, fc);
     pad_frac_kernel<<<p->chunks, PAD_THREADS, 0, st>>>(natoms, d_coords, g, p->d_frac, d_part);
-    PAD_TRY(cudaGetLastError());
+    PAD_TRY(cudaGetLastError()); kb_note_launch();
     pad_lohi_kernel<<<1, 256, 0, st>>>(p->chunks, d_part, p->d_lohi);
-    PAD_TRY(cudaGetLastError());
+    PAD_TRY(cudaGetLastError()); kb_note_launch();
     dim3 grid(p->chunks, (unsigned) p->nshift);
     pad_select_kernel<false><<<grid, PAD_THREADS, 0, st>>>(natoms, g, p->d_frac, p->d_lohi,
                                                            p->d_cnt, nullptr, nullptr, nullptr,
                                                            nullptr, nullptr);
-    PAD_TRY(cudaGetLastError());
+    PAD_TRY(cudaGetLastError()); kb_note_launch();
     rc = kb_exclusive_scan<int32_t, int64_t>(p->d_cnt, p->d_off, nblk, p->d_off + nblk, st);
     if (rc) goto fail;
     PAD_TRY(cudaMemcpyAsync(&p->npad, p->d_off + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -352,6 +352,7 @@ extern "C" int kb_pad_finish(kb_pad_plan* p, const int32_t* d_species, double* d
                                                             d_pad_image);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) rc = -(int) e;
+      else kb_note_launch();
     }
   }
   kb_pad_destroy(p, stream);

@@ -16,7 +16,7 @@ import torch
 from ... import ops
 from ...neighbor import NeighborList
 from ...packed import PackedFingerprints
-from ...utils import default_device
+from ...utils import default_device, map_species
 from .descriptor import (Descriptor, generate_full_cutoff, generate_species_code,
                          generate_unique_cutoff_pairs)
 from .hyperparams import get_set30, get_set51
@@ -89,7 +89,7 @@ class SymmetryFunction(Descriptor):
         d = nei.device_data
         n = d["n_contrib"]
         try:
-            code_cb = np.asarray([self.species_code[s] for s in conf.species], dtype=np.int32)
+            code_cb = map_species(conf.species, self.species_code)
         except KeyError as e:
             raise SymmetryFunctionError(f"species {e} not in the cutoff dictionary")
         code_cb = torch.as_tensor(code_cb, device=device)

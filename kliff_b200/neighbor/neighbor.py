@@ -13,7 +13,7 @@ import torch
 from .. import ops
 from .._lib import KB_ERR_REFERENCE, KliffB200Error
 from ..atomic_data import atomic_number, atomic_species
-from ..utils import default_device
+from ..utils import default_device, map_species
 
 
 class NeighborListError(Exception):
@@ -38,7 +38,10 @@ class NeighborList:
         coords_cb = np.ascontiguousarray(self.conf.coords, dtype=np.double).reshape(-1, 3)
         cell = np.asarray(self.conf.cell, dtype=np.double)
         pbc = np.asarray(self.conf.PBC, dtype=np.intc)
-        z_cb = np.asarray([atomic_number[s] for s in self.conf.species], dtype=np.intc)
+        try:
+            z_cb = map_species(self.conf.species, atomic_number)
+        except KeyError as e:
+            raise NeighborListError(f"unknown chemical species {e}")
         d_coords = torch.as_tensor(coords_cb, device=dev)
         d_z = torch.as_tensor(z_cb, device=dev)
         try:

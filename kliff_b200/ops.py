@@ -290,3 +290,8 @@ def probe_hbm_copy(nbytes=1 << 30):
     v = C.c_double(0.0)
     check(_lib.lib().kb_probe_hbm_copy(int(nbytes), C.byref(v), _stream()), "kb_probe_hbm_copy")
     return v.value
+
+
+def launch_count(reset=False):
+    """Kernels launched by libkliff_b200 in this process so far."""
+    return int(_lib.lib().kb_launch_count(1 if reset else 0))

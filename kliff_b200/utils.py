@@ -50,3 +50,28 @@ def default_device():
             "kliff_b200 needs a CUDA device (B200, sm_100a): the descriptor path has no CPU fallback"
         )
     return torch.device("cuda", torch.cuda.current_device())
+
+
+def map_species(species, mapping, what="species"):
+    """Vectorised `[mapping[s] for s in species]` -> int32 array (a 1M-atom configuration must
+    not cost a million dict lookups)."""
+    arr = np.asarray(species)
+    out = np.full(arr.shape[0], -1, dtype=np.int32)
+    if arr.shape[0] == 0:
+        return out
+    for name in np.unique(arr) if arr.shape[0] < 4096 else _unique_large(arr):
+        if str(name) not in mapping:
+            raise KeyError(str(name))
+        out[arr == name] = mapping[str(name)]
+    return out
+
+
+def _unique_large(arr):
+    # np.unique sorts strings; on large uniform arrays peel distinct values off one at a time
+    found, rest = [], arr
+    while rest.shape[0]:
+        found.append(rest[0])
+        rest = rest[rest != rest[0]]
+        if len(found) > 128:
+            return np.unique(arr)
+    return found

@@ -109,7 +109,7 @@ def test_symmetry_function_transform_kat():
 def test_contraction_with_ones_property():
     """tests/transformations/test_descriptors.py:14-72 (property half): tensordot(ones, dzetadr)
     equals the VJP with ones; here: dense view vs force-scatter kernel."""
-    confs = configs_from_npz("si_varying_alat.npz", limit=1)
+    confs = [configs_from_npz("si_varying_alat.npz", limit=8)[7]]  # 64 atoms, |F| up to 1.9 eV/A
     for hp, D in (("set30", 30), ("set51", 51)):
         desc = SymmetryFunction({"Si-Si": 4.5}, "cos", hp)
         zeta, dzf, _ = desc.transform(confs[0], fit_forces=True)
@@ -118,13 +118,15 @@ def test_contraction_with_ones_property():
         dense = np.tensordot(np.ones((n, D)), dzf, ([0, 1], [0, 1]))
         packed = desc.transform_packed([confs[0]])
         F = packed.forces(torch.ones((n, D), dtype=torch.float64, device=packed.device), 0, n)
-        assert np.allclose(-F.cpu().numpy(), dense, rtol=1e-10, atol=1e-10 * np.abs(dense).max())
+        # each component is a sum of ~30 x D cancelling terms: tolerance relative to the terms
+        assert np.allclose(-F.cpu().numpy(), dense, rtol=1e-10, atol=1e-10 * np.abs(dzf).max())
 
 
 def test_generate_fingerprints_normalisation(workdir):
     """tests/descriptors/test_descriptor.py:81-145: mean/stdev (np.mean/np.std), normalised zeta and
     dzetadr in the pickle, state file; both gradient formats."""
-    confs = configs_from_npz("si_varying_alat.npz", limit=3) + configs_from_npz("si_varying_alat.npz")[-2:]
+    every = configs_from_npz("si_varying_alat.npz")
+    confs = [every[i] for i in (0, 3, 7, 398, 399)]  # 8- and 64-atom cells
     raw = SymmetryFunction({"Si-Si": 5.0}, "cos", "set30", normalize=False, dtype=np.float64)
     zs = [raw.transform(c, fit_forces=True) for c in confs]
     stacked = np.concatenate([z[0] for z in zs])
@@ -163,7 +165,8 @@ def make_model(desc, n1=10, n2=10):
 
 def test_calculator_torch_parameters_and_forces(workdir):
     """tests/calculators/test_calculator_torch.py:95-162."""
-    confs = configs_from_npz("si_varying_alat.npz", limit=4)
+    every = configs_from_npz("si_varying_alat.npz", limit=52)
+    confs = [every[i] for i in (3, 7, 19, 51)]  # 64-atom cells with |F| > 1.5 eV/A
     desc = SymmetryFunction({"Si-Si": 5.0}, "cos", "set30", normalize=True)
     model = make_model(desc)
     calc = CalculatorTorch(model, gpu=False)
@@ -190,13 +193,14 @@ def test_calculator_torch_parameters_and_forces(workdir):
     dense.update_model_params(np.ones(nparams))
     out_d = dense.compute(next(iter(dense.get_compute_arguments(batch_size=4))))
     for a, b in zip(out["forces"], out_d["forces"]):
-        assert torch.allclose(a, b, rtol=2e-4, atol=2e-4 * float(b.abs().max()))
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-3 * float(b.abs().max()))
     for a, b in zip(out["energy"], out_d["energy"]):
         assert torch.allclose(a, b, rtol=1e-5)
 
 
 def test_calculator_reuse_fingerprints(workdir):
-    confs = configs_from_npz("si_varying_alat.npz", limit=3)
+    every = configs_from_npz("si_varying_alat.npz", limit=8)
+    confs = [every[i] for i in (0, 3, 7)]
     calc = CalculatorTorch(make_model(SymmetryFunction({"Si-Si": 5.0}, "cos", "set51", normalize=True)))
     calc.create(confs, fingerprints_filename="fp.pkl", fingerprints_mean_stdev_filename="ms.pkl")
     ref = calc.compute(next(iter(calc.get_compute_arguments(3))))
@@ -204,8 +208,9 @@ def test_calculator_reuse_fingerprints(workdir):
     calc2.create(confs, fingerprints_filename="fp.pkl", fingerprints_mean_stdev_filename="ms.pkl", reuse=True)
     assert np.allclose(calc2.model.descriptor.mean, calc.model.descriptor.mean)
     out = calc2.compute(next(iter(calc2.get_compute_arguments(3))))
-    for a, b in zip(ref["forces"], out["forces"]):
-        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(a.abs().max()))
+    scale = max(float(f.abs().max()) for f in ref["forces"])
+    for a, b in zip(ref["forces"], out["forces"]):  # gradients went through float32 on disk
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-4 * scale)
     from kliff_b200.legacy.calculators import CalculatorTorchError
     with pytest.raises(CalculatorTorchError):
         calc2.create(confs, fingerprints_filename="missing.pkl", reuse=True)
