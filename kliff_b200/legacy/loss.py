@@ -141,7 +141,7 @@ class LossNeuralNetworkModel:
                         return self._sync_gradients(loss)
 
                     loss = self.optimizer.step(closure)
-                    epoch_loss += float(loss)
+                    epoch_loss += float(loss.detach())
                 if chief:
                     self.calculator.save_model(epoch)
             self.epoch_losses.append(epoch_loss)
