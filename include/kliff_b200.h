@@ -140,7 +140,8 @@ void kb_nl_destroy(kb_nl_plan* plan, void* stream);
 /* ------------------------------------------------------------------------------------------ */
 #define KB_SYMFUN_AUTO 0
 #define KB_SYMFUN_GENERAL 1     /* global-atomics kernel: any neighbor count */
-#define KB_SYMFUN_TILED 2       /* shared-memory kernel: n <= 64 */
+#define KB_SYMFUN_TILED 2       /* CTA-per-atom shared-memory kernel: n <= 64, any families */
+#define KB_SYMFUN_WARP 3        /* warp-per-atom kernel: n <= 64, g1-g4 with zeta in {1,2,4,16}, lambda = +-1 */
 
 int kb_symfun_block_offsets(int32_t n_centers, const int32_t* d_centers,
                             const int64_t* d_nl_offsets, int32_t n_desc, int64_t* d_dz_ptr,

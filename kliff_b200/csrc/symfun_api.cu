@@ -12,6 +12,12 @@ int kb_symfun_tiled_launch(const kb_symfun_params& P, int n_centers, const int32
                            double* d_zeta, double* d_dz, const int64_t* d_dz_ptr,
                            int32_t* d_overflow, bool* may_overflow, cudaStream_t st);
 
+int kb_symfun_warp_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
+                          const int32_t* d_subset, const double* d_coords, const int32_t* d_species,
+                          const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn, double* d_zeta,
+                          double* d_dz, const int64_t* d_dz_ptr, int32_t* d_overflow, int full_capacity,
+                          bool* launched, bool* may_overflow, cudaStream_t st);
+
 namespace {
 
 __global__ void block_size_kernel(int n_centers, const int32_t* __restrict__ centers,
@@ -90,6 +96,50 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
     return kb_symfun_general_launch(P, n_centers, d_centers, nullptr, d_coords, d_species,
                                     d_nl_offsets, d_nl_indices, d_zeta, d_dz, d_dz_ptr, st);
 
+  // ---- preferred: warp-per-atom kernel (g4 sets with canonical exponents, n <= 64)
+  if (mode == KB_SYMFUN_AUTO || mode == KB_SYMFUN_WARP)
+  {
+    int32_t* ov = nullptr;
+    KB_CUDA(cudaMallocAsync((void**) &ov, sizeof(int32_t) * ((size_t) n_centers + 2), st));
+    KB_CUDA(cudaMemsetAsync(ov, 0, 2 * sizeof(int32_t), st));
+    bool launched = false, may_overflow = false;
+    rc = kb_symfun_warp_launch(P, n_centers, d_centers, nullptr, d_coords, d_species, d_nl_offsets,
+                               d_nl_indices, maxn, d_zeta, d_dz, d_dz_ptr, ov, 0, &launched,
+                               &may_overflow, st);
+    if (rc == KB_OK && launched && may_overflow)
+    {
+      int32_t n_over = 0;
+      cudaError_t e = cudaMemcpyAsync(&n_over, ov, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) rc = -(int) e;
+      if (rc == KB_OK && n_over > 0)
+      {
+        // second pass with worst-case record capacity over the declined atoms only
+        int32_t* ov2 = nullptr;
+        KB_CUDA(cudaMallocAsync((void**) &ov2, sizeof(int32_t) * ((size_t) n_over + 2), st));
+        KB_CUDA(cudaMemsetAsync(ov2, 0, 2 * sizeof(int32_t), st));
+        bool l2 = false, m2 = false;
+        rc = kb_symfun_warp_launch(P, n_over, d_centers, ov + 2, d_coords, d_species, d_nl_offsets,
+                                   d_nl_indices, maxn, d_zeta, d_dz, d_dz_ptr, ov2, 1, &l2, &m2, st);
+        int32_t n_over2 = l2 ? 0 : n_over;
+        if (rc == KB_OK && l2 && m2)
+        {
+          e = cudaMemcpyAsync(&n_over2, ov2, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+          if (e != cudaSuccess) rc = -(int) e;
+        }
+        if (rc == KB_OK && n_over2 > 0)  // n > 64 (or nothing fits): global-atomics kernel
+          rc = kb_symfun_general_launch(P, n_over2, d_centers, l2 ? ov2 + 2 : ov + 2, d_coords,
+                                        d_species, d_nl_offsets, d_nl_indices, d_zeta, d_dz, d_dz_ptr, st);
+        cudaFreeAsync(ov2, st);
+      }
+    }
+    cudaFreeAsync(ov, st);
+    if (rc != KB_OK || launched) return rc;
+    if (mode == KB_SYMFUN_WARP) return KB_ERR_LIMIT;  // parameter set outside the warp kernel's domain
+  }
+
+  // ---- CTA-per-atom kernel: g5 families and generic exponents
   int32_t* d_overflow = nullptr;
   KB_CUDA(cudaMallocAsync((void**) &d_overflow, sizeof(int32_t) * ((size_t) n_centers + 1), st));
   KB_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), st));

@@ -1,0 +1,478 @@
+// Warp-per-atom symmetry-function + dG/dr kernel (fp64) for sm_100a — the hot kernel, v2.
+//
+// Replaces the per-atom call chain sym_fn.py:155-160 -> Descriptor::generate_one_atom
+// (sym_fn.cpp:416-602) -> sym_d_g2 / sym_d_g4 (:627-809) for radial g1/g2/g3 and angular g4
+// sets with (zeta, lambda) in {1,2,4,16} x {-1,+1} (set51, set30 and every Behler-style set).
+// Anything else (g5, other exponents, n > 64) is declined and taken by symfun_tiled.cu /
+// symfun_general.cu.
+//
+// Why this shape (ncu evidence of the CTA-per-atom predecessor, profiles/r01_ncu_symfun_tiled_v1.txt):
+// 40 % of warp time sat in CTA barriers between the table / record / triple / copy phases, lanes were
+// 74 % utilised, and every eta-lane recomputed the triple geometry.  Here ONE WARP owns an atom end
+// to end — no __syncthreads, only __syncwarp — and 8 such warps are resident per SM, each with its
+// own ~25 KB of shared memory, so one warp's transcendental-heavy table phases overlap another
+// warp's FMA-bound triple loop on the same FP64 pipe.
+//
+// Per atom:
+//   A  pair-ij table   lanes = neighbors: r, 1/r, unit vector, fc, fc', exp(-eta_g r^2) per eta   [smem]
+//   D  radial sets     lanes = neighbors: phi, dphi -> rows written straight to global
+//   B  pair-jk test    row j, lanes = k>j: reference predicate r_jk <= rc_jk (sym_fn.cpp:729), ballot
+//                      compaction into record slots + a 64-bit adjacency mask per neighbor (no atomics:
+//                      the warp is the only writer)
+//   C  pair-jk records lanes = records: r, 1/r, fc, fc', exp(-eta_g r^2)                             [smem]
+//   S  slots sorted by adjacency degree, so that the 32/NGP slots sharing a warp-item have the same
+//      trip count (diamond Si: degrees 18/12/10 -> zero divergence)
+//   E  triple loop     item = (slot k, eta-group g), lane = (k_sub, g).  Each step, the NGP lanes of a
+//      slot first compute the geometry of NGP ordered pairs (j -> k) ONCE (cos, F, and the three
+//      3-vectors W1, P, R) into a 3 KB scratch, then every eta-lane sweeps those entries with a
+//      rank-2 update of its 8x3 register accumulators:
+//            acc[e][c] += C'_e(cos) * (e_g F W1[c]) + C_e(cos) * (E_g (eta_g P[c] + R[c]))
+//      (2 DFMA per entry-component; powers of (1 +- cos) by a multiplication chain).
+//      Only the derivative w.r.t. slot k is accumulated, so there are no write conflicts; every
+//      unordered triple is visited from both ends like the reference's slots jj/kk (:587-593).
+//   F  centre slot = -sum_k slot_k (translation invariance) and zeta = 1/2 sum over ordered pairs are
+//      carried in registers across items and reduced once per atom with xor-shuffles.
+#include "common.cuh"
+#include "symfun_math.cuh"
+
+namespace {
+
+constexpr int GW = KB_GROUP_WIDTH;
+constexpr int SCW = 12;  // doubles per scratch entry
+
+struct WarpArgs
+{
+  int n_centers;
+  const int32_t* centers;
+  const int32_t* subset;  // optional list of centre ordinals (second pass over overflow atoms)
+  const double* coords;
+  const int32_t* species;
+  const int64_t* nl_off;
+  const int32_t* nl_idx;
+  double* zeta;
+  double* dz;
+  const int64_t* dz_ptr;
+  int32_t* overflow;  // [0] count, [1] work counter, [2..] ordinals this kernel declined
+  int NP;             // neighbor capacity (even, <= 64)
+  int RC;             // pair-jk record capacity
+  int NGP;            // power of two >= n_groups, <= 32
+};
+
+__host__ __device__ inline size_t warp_smem_bytes(const kb_symfun_params& P, int NP, int RC)
+{
+  const int NG = P.n_groups, NT = P.n_two;
+  size_t d = (size_t) 3 * NP + (size_t) NP * (8 + NG) + (size_t) RC * (4 + NG) + 32 * SCW + 4 * (size_t) NT;
+  size_t bytes = d * 8 + (size_t) NP * 8;        // + adjacency masks
+  bytes += (size_t) NP * 4;                      // species
+  bytes += (size_t) (NP * NP + RC) * 2;          // pair index, pair list
+  bytes += (size_t) 2 * NP;                      // degree, slot order
+  return (bytes + 15) & ~(size_t) 15;
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(32, 8)
+symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const unsigned FULL = 0xffffffffu;
+  const int NP = A.NP, RC = A.RC, NG = P.n_groups, NGP = A.NGP, D = P.n_desc, NT = P.n_two;
+  const int SJ = 8 + NG, SR = 4 + NG;
+  const int S = P.n_species;
+
+  double* XYZ = reinterpret_cast<double*>(smem_raw);  // [3][NP]
+  double* TJ = XYZ + 3 * NP;                          // [NP][SJ]: r r2 1/r fc dfc ux uy uz x_g..
+  double* RK = TJ + NP * SJ;                          // [RC][SR]: r 1/r fc dfc x_g..
+  double* SC = RK + RC * SR;                          // [32][SCW]
+  double* Z2 = SC + 32 * SCW;                         // [NT] radial zeta, [3 NT] radial centre slot
+  unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(Z2 + 4 * NT);  // [NP]
+  int* SPC = reinterpret_cast<int*>(ADJ + NP);        // [NP]
+  unsigned short* PIDX = reinterpret_cast<unsigned short*>(SPC + NP);  // [NP][NP]
+  unsigned short* PAIR = PIDX + NP * NP;              // [RC]
+  unsigned char* DEG = reinterpret_cast<unsigned char*>(PAIR + RC);    // [NP]
+  unsigned char* KORD = DEG + NP;                     // [NP]
+
+  // ---- per-lane constants of the triple loop (the warp is persistent)
+  const int KPW = 32 / NGP;
+  const int ksub = lane / NGP, g = lane & (NGP - 1);
+  const bool valid_g = g < NG;
+  double eta = 0.0;
+  int gout[GW];
+#pragma unroll
+  for (int e = 0; e < GW; e++) gout[e] = -1;
+  if (valid_g)
+  {
+    eta = P.grp_eta[g];
+#pragma unroll
+    for (int e = 0; e < GW; e++) gout[e] = P.grp_out[g][e];
+  }
+  const double p2tab[GW] = {1.0, 1.0, 0.5, 0.5, 0.125, 0.125, 1.0 / 32768.0, 1.0 / 32768.0};
+
+  for (;;)
+  {
+    // ---- dynamic work distribution: one atom per grab
+    int t = 0;
+    if (lane == 0) t = atomicAdd(A.overflow + 1, 1);
+    t = __shfl_sync(FULL, t, 0);
+    if (t >= A.n_centers) break;
+    if (A.subset) t = A.subset[t];
+    const int i = A.centers ? A.centers[t] : t;
+    const int64_t off = A.nl_off[i];
+    const int n = (int) (A.nl_off[i + 1] - off);
+    if (n > NP)
+    {
+      if (lane == 0) A.overflow[2 + atomicAdd(A.overflow, 1)] = t;
+      continue;
+    }
+    const int si = A.species[i];
+    const double xi = A.coords[3 * i], yi = A.coords[3 * i + 1], zi = A.coords[3 * i + 2];
+    const int row = 3 * (n + 1);
+    double* blk = GRAD ? A.dz + A.dz_ptr[t] : nullptr;
+    double* zrow = A.zeta + (int64_t) t * D;
+
+    for (int q = lane; q < 4 * NT; q += 32) Z2[q] = 0.0;
+    __syncwarp();
+
+    // ---- phases A + D: pair-ij table and radial sets; lanes = neighbors ----------------------
+    unsigned long long ACT = 0ull;
+    for (int j0 = 0; j0 < n; j0 += 32)
+    {
+      const int jj = j0 + lane;
+      bool act = false;
+      double r = 1.0, fc = 0.0, dfc = 0.0, ux = 0.0, uy = 0.0, uz = 0.0;
+      if (jj < n)
+      {
+        const int j = A.nl_idx[off + jj];
+        const int sj = A.species[j];
+        const double xj = A.coords[3 * j], yj = A.coords[3 * j + 1], zj = A.coords[3 * j + 2];
+        const double vx = xsub(xj, xi), vy = xsub(yj, yi), vz = xsub(zj, zi);
+        r = sqrt(xnorm2(vx, vy, vz));   // sym_fn.cpp:447-448
+        const double rc = P.rcut[si * S + sj];
+        act = !(r > rc);                // :451
+        const double ir = 1.0 / r;
+        if (act) kb_cutoff(r, rc, fc, dfc);
+        ux = vx * ir; uy = vy * ir; uz = vz * ir;
+        XYZ[jj] = xj; XYZ[NP + jj] = yj; XYZ[2 * NP + jj] = zj;
+        SPC[jj] = sj;
+        double* tj = TJ + jj * SJ;
+        const double r2 = r * r;
+        tj[0] = r; tj[1] = r2; tj[2] = ir; tj[3] = fc; tj[4] = dfc; tj[5] = ux; tj[6] = uy; tj[7] = uz;
+        for (int q = 0; q < NG; q++) tj[8 + q] = act ? exp(-P.grp_eta[q] * r2) : 0.0;
+        ADJ[jj] = 0ull;
+      }
+      ACT |= (unsigned long long) __ballot_sync(FULL, act) << j0;
+      for (int q = 0; q < NT; q++)
+      {
+        double phi = 0.0, dphi = 0.0;
+        if (act) kb_radial(P.two_kind[q], P.two_p0[q], P.two_p1[q], r, fc, dfc, phi, dphi);
+        const double px = dphi * ux, py = dphi * uy, pz = dphi * uz;  // :497
+        if (GRAD && jj < n)
+        {
+          double* o = blk + (int64_t) P.two_out[q] * row + 3 * jj;
+          o[0] = px; o[1] = py; o[2] = pz;
+        }
+        const double s0 = warp_sum(phi);
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (GRAD) { s1 = warp_sum(px); s2 = warp_sum(py); s3 = warp_sum(pz); }
+        if (lane == 0)
+        {
+          Z2[q] += s0;
+          Z2[NT + 3 * q] += s1; Z2[NT + 3 * q + 1] += s2; Z2[NT + 3 * q + 2] += s3;
+        }
+      }
+    }
+    __syncwarp();
+    for (int q = lane; q < NT; q += 32)
+    {
+      zrow[P.two_out[q]] = Z2[q];
+      if (GRAD)
+      {
+        double* o = blk + (int64_t) P.two_out[q] * row + 3 * n;  // centre slot, :499-501
+        o[0] = -Z2[NT + 3 * q]; o[1] = -Z2[NT + 3 * q + 1]; o[2] = -Z2[NT + 3 * q + 2];
+      }
+    }
+
+    // ---- phase B: contributing neighbor pairs -> record slots + adjacency masks --------------
+    int nrec = 0;
+    for (int j = 0; j + 1 < n; j++)
+    {
+      if (!((ACT >> j) & 1ull)) continue;
+      const double xj = XYZ[j], yj = XYZ[NP + j], zj = XYZ[2 * NP + j];
+      const int sj = SPC[j];
+      for (int k0 = j + 1; k0 < n; k0 += 32)
+      {
+        const int k = k0 + lane;
+        bool hit = false;
+        if (k < n && ((ACT >> k) & 1ull))
+        {
+          const double r = sqrt(xnorm2(xsub(XYZ[k], xj), xsub(XYZ[NP + k], yj), xsub(XYZ[2 * NP + k], zj)));
+          hit = !(r > P.rcut[sj * S + SPC[k]]);  // :729 (and :541 for the ik leg)
+        }
+        const unsigned bal = __ballot_sync(FULL, hit);
+        if (hit)
+        {
+          const int slot = nrec + __popc(bal & ((1u << lane) - 1u));
+          if (slot < RC)
+          {
+            PAIR[slot] = (unsigned short) (j | (k << 8));
+            PIDX[j * NP + k] = (unsigned short) slot;
+            PIDX[k * NP + j] = (unsigned short) slot;
+          }
+          ADJ[k] |= 1ull << j;  // lane k is the only writer of ADJ[k] in this instruction
+        }
+        __syncwarp();
+        if (lane == 0) ADJ[j] |= (unsigned long long) bal << k0;
+        nrec += __popc(bal);
+        __syncwarp();
+      }
+    }
+    if (nrec > RC)
+    {
+      if (lane == 0) A.overflow[2 + atomicAdd(A.overflow, 1)] = t;
+      continue;
+    }
+
+    // ---- phase C: pair-jk records; lanes = records --------------------------------------------
+    for (int r0 = lane; r0 < nrec; r0 += 32)
+    {
+      const int j = PAIR[r0] & 0xff, k = PAIR[r0] >> 8;
+      const double r = sqrt(xnorm2(xsub(XYZ[k], XYZ[j]), xsub(XYZ[NP + k], XYZ[NP + j]),
+                                   xsub(XYZ[2 * NP + k], XYZ[2 * NP + j])));
+      double fc, dfc;
+      kb_cutoff(r, P.rcut[SPC[j] * S + SPC[k]], fc, dfc);
+      double* rk = RK + r0 * SR;
+      const double r2 = r * r;
+      rk[0] = r; rk[1] = 1.0 / r; rk[2] = fc; rk[3] = dfc;
+      for (int q = 0; q < NG; q++) rk[4 + q] = exp(-P.grp_eta[q] * r2);
+    }
+
+    // ---- phase S: slots ordered by adjacency degree (descending, index as tie-break) ---------
+    for (int k = lane; k < n; k += 32) DEG[k] = (unsigned char) __popcll(ADJ[k]);
+    __syncwarp();
+    for (int k = lane; k < n; k += 32)
+    {
+      const int dk = DEG[k];
+      int rank = 0;
+      for (int m = 0; m < n; m++) rank += (DEG[m] > dk) || (DEG[m] == dk && m < k);
+      KORD[rank] = (unsigned char) k;
+    }
+    __syncwarp();
+
+    // ---- phase E: triple loop -------------------------------------------------------------------
+    double csum[GW][3], zsum[GW];
+#pragma unroll
+    for (int e = 0; e < GW; e++) { csum[e][0] = csum[e][1] = csum[e][2] = 0.0; zsum[e] = 0.0; }
+
+    const int nwi = (n + KPW - 1) / KPW;
+    for (int wi = 0; wi < nwi; wi++)
+    {
+      const int kk = wi * KPW + ksub;
+      const bool valid_k = kk < n;
+      const int k = valid_k ? KORD[kk] : 0;
+      const double* tk = TJ + k * SJ;
+      const double rik = tk[0], rik2 = tk[1], irik = tk[2], fik = tk[3], dfik = tk[4];
+      const double ukx = tk[5], uky = tk[6], ukz = tk[7];
+      const double xk = XYZ[k], yk = XYZ[NP + k], zk = XYZ[2 * NP + k];
+      const double xik = valid_g ? tk[8 + g] : 0.0;
+      unsigned long long remaining = valid_k ? ADJ[k] : 0ull;
+
+      double acc[GW][3], phi[GW];
+#pragma unroll
+      for (int e = 0; e < GW; e++) { acc[e][0] = acc[e][1] = acc[e][2] = 0.0; phi[e] = 0.0; }
+
+      while (__any_sync(FULL, remaining != 0ull))
+      {
+        // geometry of up to NGP ordered pairs (j -> k) per slot: lane g takes the g-th set bit
+        unsigned long long m = remaining;
+        for (int q = 0; q < g; q++) m &= m - 1ull;
+        if (m != 0ull)
+        {
+          const int j = __ffsll((long long) m) - 1;
+          const int rec = PIDX[k * NP + j];
+          const double* tj = TJ + j * SJ;
+          const double* rk = RK + rec * SR;
+          const double rij = tj[0], rij2 = tj[1], irij = tj[2], fij = tj[3];
+          const double rjk = rk[0], irjk = rk[1], fjk = rk[2], dfjk = rk[3];
+          const double wx = (xk - XYZ[j]) * irjk, wy = (yk - XYZ[NP + j]) * irjk,
+                       wz = (zk - XYZ[2 * NP + j]) * irjk;      // unit vector j -> k
+          const double rjk2 = rjk * rjk;
+          const double h = 0.5 * irij * irik;
+          const double ct = (rij2 + rik2 - rjk2) * h;            // cos(theta_jik), :744
+          const double dct_ik = (rik2 - rij2 + rjk2) * h * irik;  // :746
+          const double dct_jk = -2.0 * rjk * h;                   // :747
+          const double fijk = fij * fjk;
+          const double F = fijk * fik;
+          const double dF_ik = dfik * fijk, dF_jk = dfjk * (fij * fik);
+          const double a = -2.0 * F * rik, b = -2.0 * F * rjk;
+          double* sc = SC + lane * SCW;
+          sc[0] = ct;
+          sc[1] = F;
+          sc[2] = dct_ik * ukx + dct_jk * wx; sc[3] = dct_ik * uky + dct_jk * wy; sc[4] = dct_ik * ukz + dct_jk * wz;
+          sc[5] = a * ukx + b * wx;           sc[6] = a * uky + b * wy;           sc[7] = a * ukz + b * wz;
+          sc[8] = dF_ik * ukx + dF_jk * wx;   sc[9] = dF_ik * uky + dF_jk * wy;   sc[10] = dF_ik * ukz + dF_jk * wz;
+          sc[11] = __hiloint2double(rec, j);
+        }
+        const int have = __popcll(remaining);
+        const int cnt = have < NGP ? have : NGP;
+        for (int q = 0; q < NGP; q++) remaining &= remaining - 1ull;  // no-op once empty
+        const int maxcnt = __reduce_max_sync(FULL, cnt);
+        __syncwarp();
+
+        for (int ej = 0; ej < maxcnt; ej++)
+        {
+          if (ej < cnt && valid_g)
+          {
+            const double* sc = SC + (ksub * NGP + ej) * SCW;
+            const double ct = sc[0], F = sc[1];
+            const int j = __double2loint(sc[11]), rec = __double2hiint(sc[11]);
+            const double E = TJ[j * SJ + 8 + g] * xik * RK[rec * SR + 4 + g];
+            const double eF = E * F, Ee = E * eta;
+            const double v1x = eF * sc[2], v1y = eF * sc[3], v1z = eF * sc[4];
+            const double v2x = fma(Ee, sc[5], E * sc[8]), v2y = fma(Ee, sc[6], E * sc[9]),
+                         v2z = fma(Ee, sc[7], E * sc[10]);
+            double C[GW], Cp[GW];
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+            {
+              const double lam = s ? 1.0 : -1.0;
+              double bse = fma(lam, ct, 1.0);
+              const bool ok = bse > 0.0;  // guard of :755-767
+              bse = ok ? bse : 0.0;
+              const double b2 = bse * bse, b3 = b2 * bse, b4 = b2 * b2, b8 = b4 * b4;
+              const double b16 = b8 * b8, b15 = b8 * b4 * b3;
+              C[0 + s] = bse; Cp[0 + s] = ok ? lam : 0.0;
+              C[2 + s] = b2;  Cp[2 + s] = 2.0 * lam * bse;
+              C[4 + s] = b4;  Cp[4 + s] = 4.0 * lam * b3;
+              C[6 + s] = b16; Cp[6 + s] = 16.0 * lam * b15;
+            }
+#pragma unroll
+            for (int e = 0; e < GW; e++)
+            {
+              phi[e] = fma(C[e], eF, phi[e]);
+              if (GRAD)
+              {
+                acc[e][0] = fma(C[e], v2x, fma(Cp[e], v1x, acc[e][0]));
+                acc[e][1] = fma(C[e], v2y, fma(Cp[e], v1y, acc[e][1]));
+                acc[e][2] = fma(C[e], v2z, fma(Cp[e], v1z, acc[e][2]));
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+
+      // item done: write slot k's rows, fold into the per-atom partial sums
+      if (valid_k && valid_g)
+      {
+#pragma unroll
+        for (int e = 0; e < GW; e++)
+        {
+          zsum[e] += phi[e];
+          if (GRAD)
+          {
+            csum[e][0] += acc[e][0]; csum[e][1] += acc[e][1]; csum[e][2] += acc[e][2];
+            if (gout[e] >= 0)
+            {
+              double* o = blk + (int64_t) gout[e] * row + 3 * k;
+              o[0] = p2tab[e] * acc[e][0]; o[1] = p2tab[e] * acc[e][1]; o[2] = p2tab[e] * acc[e][2];
+            }
+          }
+        }
+      }
+    }
+
+    // ---- phase F: centre slot (translation invariance) and zeta, reduced over the slot lanes ----
+#pragma unroll
+    for (int e = 0; e < GW; e++)
+    {
+      for (int m = NGP; m < 32; m <<= 1)
+      {
+        zsum[e] += shfl_xor_d(zsum[e], m);
+        if (GRAD)
+        {
+          csum[e][0] += shfl_xor_d(csum[e][0], m);
+          csum[e][1] += shfl_xor_d(csum[e][1], m);
+          csum[e][2] += shfl_xor_d(csum[e][2], m);
+        }
+      }
+      if (ksub == 0 && gout[e] >= 0)
+      {
+        zrow[gout[e]] = 0.5 * p2tab[e] * zsum[e];  // each unordered triple was visited twice
+        if (GRAD)
+        {
+          double* o = blk + (int64_t) gout[e] * row + 3 * n;
+          o[0] = -p2tab[e] * csum[e][0]; o[1] = -p2tab[e] * csum[e][1]; o[2] = -p2tab[e] * csum[e][2];
+        }
+      }
+    }
+    if (GRAD)
+    {
+      const int len = (int) (A.dz_ptr[t + 1] - A.dz_ptr[t]);
+      for (int q = D * row + lane; q < len; q += 32) blk[q] = 0.0;  // alignment padding
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+// Returns KB_OK and *launched = true when the parameter set is one this kernel handles.
+int kb_symfun_warp_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
+                          const int32_t* d_subset, const double* d_coords, const int32_t* d_species,
+                          const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn, double* d_zeta,
+                          double* d_dz, const int64_t* d_dz_ptr, int32_t* d_overflow, int full_capacity,
+                          bool* launched, bool* may_overflow, cudaStream_t st)
+{
+  *launched = false;
+  *may_overflow = false;
+  if (n_centers <= 0) return KB_OK;
+  if (!P.canonical_zl || P.n_groups < 1) return KB_OK;
+  for (int g = 0; g < P.n_groups; g++)
+    if (P.grp_kind[g] != KB_G4) return KB_OK;
+  int NGP = 1;
+  while (NGP < P.n_groups) NGP <<= 1;
+  if (NGP > 32) return KB_OK;
+  int NP = maxn < 2 ? 2 : maxn;
+  if (NP > 64) { NP = 64; *may_overflow = true; }
+  NP = (NP + 1) & ~1;
+  const int worst = NP * (NP - 1) / 2;
+  // Record capacity: the number of neighbor pairs within the cutoff of each other is ~45 % of all
+  // pairs for a sphere; reserve 55 % (rounded up) unless asked for the worst case.  Atoms that
+  // exceed it are redone by the caller with full capacity.
+  int RC = full_capacity ? worst : ((worst * 11 / 20 + 15) & ~15);
+  if (RC < 64) RC = worst < 64 ? (worst > 0 ? worst : 1) : 64;
+  if (RC > worst) RC = worst > 0 ? worst : 1;
+  const size_t limit = 227 * 1024;
+  while (RC > 32 && warp_smem_bytes(P, NP, RC) > limit) RC = RC * 3 / 4;
+  if (RC < worst) *may_overflow = true;
+  const size_t smem = warp_smem_bytes(P, NP, RC);
+  if (smem > limit) return KB_OK;
+
+  WarpArgs A;
+  A.n_centers = n_centers; A.centers = d_centers; A.subset = d_subset; A.coords = d_coords;
+  A.species = d_species; A.nl_off = d_nl_off; A.nl_idx = d_nl_idx; A.zeta = d_zeta; A.dz = d_dz;
+  A.dz_ptr = d_dz_ptr; A.overflow = d_overflow; A.NP = NP; A.RC = RC; A.NGP = NGP;
+
+  int dev = 0, sms = 148;
+  KB_CUDA(cudaGetDevice(&dev));
+  KB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int per_sm = (int) ((limit + 1024) / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  int grid = sms * per_sm;
+  if (grid > n_centers) grid = n_centers;
+  const bool grad = d_dz != nullptr;
+  if (grad)
+  {
+    KB_CUDA(cudaFuncSetAttribute(symfun_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    symfun_warp_kernel<true><<<grid, 32, smem, st>>>(P, A);
+  }
+  else
+  {
+    KB_CUDA(cudaFuncSetAttribute(symfun_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    symfun_warp_kernel<false><<<grid, 32, smem, st>>>(P, A);
+  }
+  KB_LAUNCH_CHECK();
+  *launched = true;
+  return KB_OK;
+}

@@ -144,7 +144,7 @@ def test_neighbor_errors(dev):
 
 
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode", [_lib.KB_SYMFUN_TILED, _lib.KB_SYMFUN_GENERAL])
+@pytest.mark.parametrize("mode", [_lib.KB_SYMFUN_AUTO, _lib.KB_SYMFUN_TILED, _lib.KB_SYMFUN_GENERAL])
 @pytest.mark.parametrize("name", RUNS)
 def test_symfun_vs_recorded_reference(dev, port, name, mode):
     g = load_golden(name)
@@ -204,7 +204,8 @@ def test_kat_symmetry_function(dev):
 
 
 @pytest.mark.parametrize("hpname", ["set51", "set30"])
-def test_symfun_512_atoms_vs_oracle(dev, port, hpname):
+@pytest.mark.parametrize("mode", [_lib.KB_SYMFUN_WARP, _lib.KB_SYMFUN_TILED])
+def test_symfun_512_atoms_vs_oracle(dev, port, hpname, mode):
     """4x4x4 jittered diamond (512 atoms, 1 600+ paddings): every block against the oracle."""
     hp = get_set51() if hpname == "set51" else get_set30()
     rng = np.random.default_rng(5)
@@ -227,7 +228,10 @@ def test_symfun_512_atoms_vs_oracle(dev, port, hpname):
     P = ops.build_params(hp, rc)
     code = torch.zeros(len(allc), dtype=torch.int32, device=dev)
     zeta, dz, dz_ptr = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
-                                          n_centers=512)
+                                          n_centers=512, mode=mode)
+    zeta0, _, _ = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
+                                     n_centers=512, grad=False, mode=mode)
+    assert torch.allclose(zeta0, zeta, rtol=1e-13, atol=0)
     oz, og = port.symfun_range(rc, orc.fams_from_hyperparams(hp), 0, 512, allc,
                                np.zeros(len(allc), np.int32), oo, oi)
     assert np.max(np.abs(zeta.cpu().numpy() - oz) / np.abs(oz)) <= TOL
