@@ -39,6 +39,9 @@ namespace {
 
 constexpr int GW = KB_GROUP_WIDTH;
 constexpr int SCW = 12;  // doubles per scratch entry
+// scratch: 32 entries; each group of NGP entries is followed by 2 doubles of padding so that the
+// 32/NGP groups, which are read simultaneously (broadcast inside a group), fall on different banks
+constexpr int SC_DOUBLES = 32 * SCW + 2 * 32;
 
 struct WarpArgs
 {
@@ -61,11 +64,11 @@ struct WarpArgs
 __host__ __device__ inline size_t warp_smem_bytes(const kb_symfun_params& P, int NP, int RC)
 {
   const int NG = P.n_groups, NT = P.n_two;
-  size_t d = (size_t) 3 * NP + (size_t) NP * (8 + NG) + (size_t) RC * (4 + NG) + 32 * SCW + 4 * (size_t) NT;
+  size_t d = (size_t) 3 * NP + (size_t) NP * (8 + NG) + (size_t) RC * (4 + NG) + SC_DOUBLES + 4 * (size_t) NT;
   size_t bytes = d * 8 + (size_t) NP * 8;        // + adjacency masks
-  bytes += (size_t) NP * 4;                      // species
-  bytes += (size_t) (NP * NP + RC) * 2;          // pair index, pair list
-  bytes += (size_t) 2 * NP;                      // degree, slot order
+  bytes += (size_t) NP * 8;                      // species, record base
+  bytes += (size_t) (NP * NP + RC) * 2;          // per-slot record lists, pair list
+  bytes += (size_t) NP * NP + 2 * (size_t) NP;   // per-slot neighbor lists, degree, slot order
   return (bytes + 15) & ~(size_t) 15;
 }
 
@@ -84,12 +87,14 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
   double* TJ = XYZ + 3 * NP;                          // [NP][SJ]: r r2 1/r fc dfc ux uy uz x_g..
   double* RK = TJ + NP * SJ;                          // [RC][SR]: r 1/r fc dfc x_g..
   double* SC = RK + RC * SR;                          // [32][SCW]
-  double* Z2 = SC + 32 * SCW;                         // [NT] radial zeta, [3 NT] radial centre slot
+  double* Z2 = SC + SC_DOUBLES;                       // [NT] radial zeta, [3 NT] radial centre slot
   unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(Z2 + 4 * NT);  // [NP]
   int* SPC = reinterpret_cast<int*>(ADJ + NP);        // [NP]
-  unsigned short* PIDX = reinterpret_cast<unsigned short*>(SPC + NP);  // [NP][NP]
-  unsigned short* PAIR = PIDX + NP * NP;              // [RC]
-  unsigned char* DEG = reinterpret_cast<unsigned char*>(PAIR + RC);    // [NP]
+  int* BASE = SPC + NP;                               // [NP] first record slot of row j (pairs j<k)
+  unsigned short* JR = reinterpret_cast<unsigned short*>(BASE + NP);   // [NP][NP] record of (slot, idx)
+  unsigned short* PAIR = JR + NP * NP;                // [RC]
+  unsigned char* JL = reinterpret_cast<unsigned char*>(PAIR + RC);     // [NP][NP] idx-th neighbor of slot
+  unsigned char* DEG = JL + NP * NP;                  // [NP]
   unsigned char* KORD = DEG + NP;                     // [NP]
 
   // ---- per-lane constants of the triple loop (the warp is persistent)
@@ -157,8 +162,12 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
         double* tj = TJ + jj * SJ;
         const double r2 = r * r;
         tj[0] = r; tj[1] = r2; tj[2] = ir; tj[3] = fc; tj[4] = dfc; tj[5] = ux; tj[6] = uy; tj[7] = uz;
-        for (int q = 0; q < NG; q++) tj[8 + q] = act ? exp(-P.grp_eta[q] * r2) : 0.0;
-        ADJ[jj] = 0ull;
+        for (int q0 = 0; q0 < NG; q0 += 8)
+        {
+#pragma unroll
+          for (int u = 0; u < 8; u++)  // independent exponentials: let them overlap
+            if (q0 + u < NG) tj[8 + q0 + u] = act ? exp(-P.grp_eta[q0 + u] * r2) : 0.0;
+        }
       }
       ACT |= (unsigned long long) __ballot_sync(FULL, act) << j0;
       for (int q = 0; q < NT; q++)
@@ -192,45 +201,69 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       }
     }
 
-    // ---- phase B: contributing neighbor pairs -> record slots + adjacency masks --------------
+    // ---- phase B: contributing neighbor pairs.  Lane = row j computes its whole adjacency row in
+    //      registers (no ballots, no atomics); the reference predicate !(sqrt(r2) > rc) (:729) is
+    //      decided on r2 whenever that is unambiguous and by the square root otherwise.
     int nrec = 0;
-    for (int j = 0; j + 1 < n; j++)
+    for (int j0 = 0; j0 < n; j0 += 32)
     {
-      if (!((ACT >> j) & 1ull)) continue;
-      const double xj = XYZ[j], yj = XYZ[NP + j], zj = XYZ[2 * NP + j];
-      const int sj = SPC[j];
-      for (int k0 = j + 1; k0 < n; k0 += 32)
+      const int j = j0 + lane;
+      unsigned long long mask = 0ull;
+      if (j < n && ((ACT >> j) & 1ull))
       {
-        const int k = k0 + lane;
-        bool hit = false;
-        if (k < n && ((ACT >> k) & 1ull))
+        const double xj = XYZ[j], yj = XYZ[NP + j], zj = XYZ[2 * NP + j];
+        const double* rcrow = P.rcut + SPC[j] * S;
+        for (int k = 0; k < n; k++)
         {
-          const double r = sqrt(xnorm2(xsub(XYZ[k], xj), xsub(XYZ[NP + k], yj), xsub(XYZ[2 * NP + k], zj)));
-          hit = !(r > P.rcut[sj * S + SPC[k]]);  // :729 (and :541 for the ik leg)
+          const double r2 = xnorm2(xsub(XYZ[k], xj), xsub(XYZ[NP + k], yj), xsub(XYZ[2 * NP + k], zj));
+          const double rc = rcrow[SPC[k]];
+          const double rc2 = rc * rc;
+          bool hit = r2 < rc2 * (1.0 - 1e-12);
+          if (!hit && r2 <= rc2 * (1.0 + 1e-12)) hit = !(sqrt(r2) > rc);
+          if (hit && k != j && ((ACT >> k) & 1ull)) mask |= 1ull << k;
         }
-        const unsigned bal = __ballot_sync(FULL, hit);
-        if (hit)
-        {
-          const int slot = nrec + __popc(bal & ((1u << lane) - 1u));
-          if (slot < RC)
-          {
-            PAIR[slot] = (unsigned short) (j | (k << 8));
-            PIDX[j * NP + k] = (unsigned short) slot;
-            PIDX[k * NP + j] = (unsigned short) slot;
-          }
-          ADJ[k] |= 1ull << j;  // lane k is the only writer of ADJ[k] in this instruction
-        }
-        __syncwarp();
-        if (lane == 0) ADJ[j] |= (unsigned long long) bal << k0;
-        nrec += __popc(bal);
-        __syncwarp();
       }
+      const int upper = (j < 63) ? __popcll(mask >> (j + 1)) : 0;
+      int inc = upper;  // inclusive warp scan of the per-row record counts
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const int y = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += y;
+      }
+      if (j < n)
+      {
+        ADJ[j] = mask;
+        DEG[j] = (unsigned char) __popcll(mask);
+        BASE[j] = nrec + inc - upper;
+      }
+      nrec += __shfl_sync(FULL, inc, 31);
     }
     if (nrec > RC)
     {
       if (lane == 0) A.overflow[2 + atomicAdd(A.overflow, 1)] = t;
       continue;
     }
+    __syncwarp();
+    // per-slot neighbor lists (ascending) with their record ids, and the (j<k) pair list
+    for (int k = lane; k < n; k += 32)
+    {
+      unsigned long long m = ADJ[k];
+      int idx = 0;
+      while (m)
+      {
+        const int j = __ffsll((long long) m) - 1;
+        m &= m - 1ull;
+        const int a = j < k ? j : k, b = j < k ? k : j;
+        const unsigned long long between = (ADJ[a] >> (a + 1)) & ((1ull << (b - a - 1)) - 1ull);
+        const int slot = BASE[a] + __popcll(between);
+        JL[k * NP + idx] = (unsigned char) j;
+        JR[k * NP + idx] = (unsigned short) slot;
+        if (j > k) PAIR[slot] = (unsigned short) (k | (j << 8));
+        idx++;
+      }
+    }
+    __syncwarp();
 
     // ---- phase C: pair-jk records; lanes = records --------------------------------------------
     for (int r0 = lane; r0 < nrec; r0 += 32)
@@ -243,12 +276,15 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       double* rk = RK + r0 * SR;
       const double r2 = r * r;
       rk[0] = r; rk[1] = 1.0 / r; rk[2] = fc; rk[3] = dfc;
-      for (int q = 0; q < NG; q++) rk[4 + q] = exp(-P.grp_eta[q] * r2);
+      for (int q0 = 0; q0 < NG; q0 += 8)
+      {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (q0 + u < NG) rk[4 + q0 + u] = exp(-P.grp_eta[q0 + u] * r2);
+      }
     }
 
     // ---- phase S: slots ordered by adjacency degree (descending, index as tie-break) ---------
-    for (int k = lane; k < n; k += 32) DEG[k] = (unsigned char) __popcll(ADJ[k]);
-    __syncwarp();
     for (int k = lane; k < n; k += 32)
     {
       const int dk = DEG[k];
@@ -274,24 +310,26 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       const double ukx = tk[5], uky = tk[6], ukz = tk[7];
       const double xk = XYZ[k], yk = XYZ[NP + k], zk = XYZ[2 * NP + k];
       const double xik = valid_g ? tk[8 + g] : 0.0;
-      unsigned long long remaining = valid_k ? ADJ[k] : 0ull;
+      const int degk = valid_k ? DEG[k] : 0;
+      const int maxdeg = __reduce_max_sync(FULL, degk);
+      const unsigned char* jl = JL + k * NP;
+      const unsigned short* jr = JR + k * NP;
+      double* scg = SC + ksub * (NGP * SCW + 2);  // this slot's scratch group
 
       double acc[GW][3], phi[GW];
 #pragma unroll
       for (int e = 0; e < GW; e++) { acc[e][0] = acc[e][1] = acc[e][2] = 0.0; phi[e] = 0.0; }
 
-      while (__any_sync(FULL, remaining != 0ull))
+      for (int s0 = 0; s0 < maxdeg; s0 += NGP)
       {
-        // geometry of up to NGP ordered pairs (j -> k) per slot: lane g takes the g-th set bit
-        unsigned long long m = remaining;
-        for (int q = 0; q < g; q++) m &= m - 1ull;
-        if (m != 0ull)
+        // geometry of up to NGP ordered pairs (j -> k) per slot: lane g takes list entry s0 + g
+        if (s0 + g < degk)
         {
-          const int j = __ffsll((long long) m) - 1;
-          const int rec = PIDX[k * NP + j];
+          const int j = jl[s0 + g];
+          const int rec = jr[s0 + g];
           const double* tj = TJ + j * SJ;
           const double* rk = RK + rec * SR;
-          const double rij = tj[0], rij2 = tj[1], irij = tj[2], fij = tj[3];
+          const double rij2 = tj[1], irij = tj[2], fij = tj[3];
           const double rjk = rk[0], irjk = rk[1], fjk = rk[2], dfjk = rk[3];
           const double wx = (xk - XYZ[j]) * irjk, wy = (yk - XYZ[NP + j]) * irjk,
                        wz = (zk - XYZ[2 * NP + j]) * irjk;      // unit vector j -> k
@@ -304,7 +342,7 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
           const double F = fijk * fik;
           const double dF_ik = dfik * fijk, dF_jk = dfjk * (fij * fik);
           const double a = -2.0 * F * rik, b = -2.0 * F * rjk;
-          double* sc = SC + lane * SCW;
+          double* sc = scg + g * SCW;
           sc[0] = ct;
           sc[1] = F;
           sc[2] = dct_ik * ukx + dct_jk * wx; sc[3] = dct_ik * uky + dct_jk * wy; sc[4] = dct_ik * ukz + dct_jk * wz;
@@ -312,9 +350,8 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
           sc[8] = dF_ik * ukx + dF_jk * wx;   sc[9] = dF_ik * uky + dF_jk * wy;   sc[10] = dF_ik * ukz + dF_jk * wz;
           sc[11] = __hiloint2double(rec, j);
         }
-        const int have = __popcll(remaining);
-        const int cnt = have < NGP ? have : NGP;
-        for (int q = 0; q < NGP; q++) remaining &= remaining - 1ull;  // no-op once empty
+        const int left = degk - s0;
+        const int cnt = left < 0 ? 0 : (left < NGP ? left : NGP);
         const int maxcnt = __reduce_max_sync(FULL, cnt);
         __syncwarp();
 
@@ -322,7 +359,7 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
         {
           if (ej < cnt && valid_g)
           {
-            const double* sc = SC + (ksub * NGP + ej) * SCW;
+            const double* sc = scg + ej * SCW;
             const double ct = sc[0], F = sc[1];
             const int j = __double2loint(sc[11]), rec = __double2hiint(sc[11]);
             const double E = TJ[j * SJ + 8 + g] * xik * RK[rec * SR + 4 + g];
