@@ -20,6 +20,78 @@ __device__ __forceinline__ void kb_cutoff(double r, double rc, double& fc, doubl
   }
 }
 
+// ---- branch-free elementary functions for the table phases ---------------------------------
+// The library exp / sincos carry special-case branches (huge arguments, NaN, Payne-Hanek), which
+// split the instruction stream into basic blocks and keep the compiler from overlapping the 7
+// independent exponentials of a pair.  On this path the arguments are bounded (x <= 0 for the
+// Gaussians, 0 <= r/rc <= 1 for the cutoff), so straight-line versions suffice; both are accurate
+// to ~2 ulp (tests compare against the reference at 1e-10).
+
+// exp(x) for x <= ~1; tends to 0 smoothly for very negative x.
+__device__ __forceinline__ double kb_exp_neg(double x)
+{
+  const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
+  const double t = fma(x, 1.4426950408889634, SHIFT);
+  int n = __double2loint(t);
+  const double nf = t - SHIFT;
+  double f = fma(nf, -6.93147180369123816490e-01, x);  // Cody-Waite, ln2 = hi + lo
+  f = fma(nf, -1.90821492927058770002e-10, f);
+  double p = 2.08767569878680989792e-09;  // 1/12!
+  p = fma(p, f, 2.50521083854417187751e-08);
+  p = fma(p, f, 2.75573192239858906526e-07);
+  p = fma(p, f, 2.75573192239858906526e-06);
+  p = fma(p, f, 2.48015873015873015873e-05);
+  p = fma(p, f, 1.98412698412698412698e-04);
+  p = fma(p, f, 1.38888888888888888889e-03);
+  p = fma(p, f, 8.33333333333333333333e-03);
+  p = fma(p, f, 4.16666666666666666667e-02);
+  p = fma(p, f, 1.66666666666666666667e-01);
+  p = fma(p, f, 0.5);
+  p = fma(p, f, 1.0);
+  p = fma(p, f, 1.0);
+  n = n < -1021 ? -1021 : n;  // exp underflows to ~1e-308 instead of wrapping the exponent field
+  return p * __hiloint2double((n + 1023) << 20, 0);
+}
+
+// sin(pi y), cos(pi y) for 0 <= y <= 1 (also fine slightly outside).
+__device__ __forceinline__ void kb_sincospi01(double y, double& s, double& c)
+{
+  const double q = rint(y + y);              // quadrant 0, 1, 2
+  const double w = (y - 0.5 * q) * KB_PI;    // |w| <= pi/4
+  const double w2 = w * w;
+  double ps = -7.64716373181981647590e-13;   // sin: w - w^3/3! + ... - w^15/15!
+  ps = fma(ps, w2, 1.60590438368216145994e-10);
+  ps = fma(ps, w2, -2.50521083854417187751e-08);
+  ps = fma(ps, w2, 2.75573192239858906526e-06);
+  ps = fma(ps, w2, -1.98412698412698412698e-04);
+  ps = fma(ps, w2, 8.33333333333333333333e-03);
+  ps = fma(ps, w2, -1.66666666666666666667e-01);
+  ps = fma(ps * w2, w, w);
+  double pc = 4.77947733238738529744e-14;    // cos: 1 - w^2/2! + ... + w^16/16!
+  pc = fma(pc, w2, -1.14707455977297247139e-11);
+  pc = fma(pc, w2, 2.08767569878680989792e-09);
+  pc = fma(pc, w2, -2.75573192239858906526e-07);
+  pc = fma(pc, w2, 2.48015873015873015873e-05);
+  pc = fma(pc, w2, -1.38888888888888888889e-03);
+  pc = fma(pc, w2, 4.16666666666666666667e-02);
+  pc = fma(pc, w2, -0.5);
+  pc = fma(pc, w2, 1.0);
+  const bool odd = (q == 1.0);
+  const double sg = (q == 2.0) ? -1.0 : 1.0;
+  s = odd ? pc : sg * ps;          // sin(w + q pi/2)
+  c = odd ? -ps : sg * pc;         // cos(w + q pi/2)
+}
+
+// cos cutoff from a precomputed 1/rc (table phases); same definition as kb_cutoff.
+__device__ __forceinline__ void kb_cutoff_fast(double r, double rc, double& fc, double& dfc)
+{
+  double s, c;
+  kb_sincospi01(r / rc, s, c);
+  const bool in = r < rc;
+  fc = in ? 0.5 * (c + 1.0) : 0.0;
+  dfc = in ? -0.5 * KB_PI / rc * s : 0.0;
+}
+
 // radial families g1/g2/g3, sym_fn.cpp:604-674.  Caller guarantees r <= rc (sym_fn.cpp:451).
 __device__ __forceinline__ void kb_radial(int kind, double p0, double p1, double r, double fc,
                                           double dfc, double& phi, double& dphi)

@@ -155,7 +155,8 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
         const double rc = P.rcut[si * S + sj];
         act = !(r > rc);                // :451
         const double ir = 1.0 / r;
-        if (act) kb_cutoff(r, rc, fc, dfc);
+        kb_cutoff_fast(r, rc, fc, dfc);
+        if (!act) { fc = 0.0; dfc = 0.0; }
         ux = vx * ir; uy = vy * ir; uz = vz * ir;
         XYZ[jj] = xj; XYZ[NP + jj] = yj; XYZ[2 * NP + jj] = zj;
         SPC[jj] = sj;
@@ -166,7 +167,7 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
         {
 #pragma unroll
           for (int u = 0; u < 8; u++)  // independent exponentials: let them overlap
-            if (q0 + u < NG) tj[8 + q0 + u] = act ? exp(-P.grp_eta[q0 + u] * r2) : 0.0;
+            if (q0 + u < NG) tj[8 + q0 + u] = act ? kb_exp_neg(-P.grp_eta[q0 + u] * r2) : 0.0;
         }
       }
       ACT |= (unsigned long long) __ballot_sync(FULL, act) << j0;
@@ -272,7 +273,7 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       const double r = sqrt(xnorm2(xsub(XYZ[k], XYZ[j]), xsub(XYZ[NP + k], XYZ[NP + j]),
                                    xsub(XYZ[2 * NP + k], XYZ[2 * NP + j])));
       double fc, dfc;
-      kb_cutoff(r, P.rcut[SPC[j] * S + SPC[k]], fc, dfc);
+      kb_cutoff_fast(r, P.rcut[SPC[j] * S + SPC[k]], fc, dfc);
       double* rk = RK + r0 * SR;
       const double r2 = r * r;
       rk[0] = r; rk[1] = 1.0 / r; rk[2] = fc; rk[3] = dfc;
@@ -280,7 +281,7 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       {
 #pragma unroll
         for (int u = 0; u < 8; u++)
-          if (q0 + u < NG) rk[4 + q0 + u] = exp(-P.grp_eta[q0 + u] * r2);
+          if (q0 + u < NG) rk[4 + q0 + u] = kb_exp_neg(-P.grp_eta[q0 + u] * r2);
       }
     }
 
