@@ -347,11 +347,11 @@ def main():
                    "l2": "256 MiB write between timed steps (outside the step's CUDA events)",
                    "step_breakdown_ms": {"paddings+neighbors": float(np.mean(nl_ms)),
                                          "symfun+dG/dr": float(np.mean(sym_ms))}},
-        "roofline": {"kernel": "symfun_tiled_kernel<1,true>", "bound": "hbm", "achieved": ach_gbs,
+        "roofline": {"kernel": "symfun_warp_kernel<true>", "bound": "hbm", "achieved": ach_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
                      "peak_source": peak_src,
                      "note": "algorithmic bytes 36 724 B/atom; the kernel is FP64-pipe bound, see roofline_fp64"},
-        "roofline_fp64": {"kernel": "symfun_tiled_kernel<1,true>", "bound": "fp64", "achieved": ach_tf,
+        "roofline_fp64": {"kernel": "symfun_warp_kernel<true>", "bound": "fp64", "achieved": ach_tf,
                           "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                           "peak_source": "DFMA-chain probe in this run (kb_probe_fp64_peak)",
                           "note": "canonical 380 618 flop/atom (SURVEY.md §8d)"},
