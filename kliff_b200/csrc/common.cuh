@@ -27,6 +27,12 @@ void kb_note_launch(int n = 1);
 
 static inline cudaStream_t kb_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
+// Scratch comes from the stream-ordered allocator.  Its default pool gives memory back to the
+// driver at every synchronisation (release threshold 0), which turns each *_begin call into
+// fresh cudaMalloc-class allocations (measured: 23 ms per 1M-atom neighbor build instead of 2 ms).
+// Keep freed scratch cached in the pool instead.  Idempotent and thread-safe.
+void kb_pool_setup();
+
 // ---- IEEE-exact, never-contracted double arithmetic --------------------------------------
 // The integer outputs (padding selection, neighbor sets) must equal the reference's bit for
 // bit, and the reference is built without FMA (x86-64 -O2).  nvcc contracts a*b+c into DFMA by

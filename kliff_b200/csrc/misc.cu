@@ -6,6 +6,22 @@
 static std::atomic<long long> g_launches{0};
 void kb_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+void kb_pool_setup()
+{
+  static std::atomic<unsigned long long> done_mask{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  const unsigned long long bit = 1ull << dev;
+  if (done_mask.load(std::memory_order_acquire) & bit) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+  {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_mask.fetch_or(bit, std::memory_order_release);
+}
+
 extern "C" int64_t kb_launch_count(int32_t reset)
 {
   return reset ? g_launches.exchange(0) : g_launches.load();

@@ -269,6 +269,7 @@ extern "C" int kb_nl_begin(int32_t ntot, int32_t n_need, const double* d_coords,
   *h_total = 0;
   *h_maxn = 0;
   cudaStream_t st = kb_stream(stream);
+  kb_pool_setup();
   kb_nl_plan* p = new (std::nothrow) kb_nl_plan();
   if (!p) return KB_ERR_INVALID;
   p->ntot = ntot; p->n_need = n_need; p->half = half; p->d_coords = d_coords; p->d_need = d_need;

@@ -260,6 +260,7 @@ extern "C" int kb_pad_begin(int32_t natoms, double cutoff, const double* h_cell,
   *out_plan = nullptr;
   *h_npad = 0;
   cudaStream_t st = kb_stream(stream);
+  kb_pool_setup();
 
   // lattice analysis on the host, same operation order as neighbor_list.cpp:291-365
   double tc[9], fc[9];

@@ -60,6 +60,7 @@ extern "C" int kb_symfun_block_offsets(int32_t n_centers, const int32_t* d_cente
 {
   if (n_centers < 0 || !d_dz_ptr || !h_total || n_desc < 1) return KB_ERR_INVALID;
   cudaStream_t st = kb_stream(stream);
+  kb_pool_setup();
   *h_total = 0;
   if (n_centers == 0)
   {
@@ -90,6 +91,7 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
   if (n_centers < 0 || !d_zeta || (d_dz && !d_dz_ptr) || maxn < 0) return KB_ERR_INVALID;
   if (n_centers == 0) return KB_OK;
   cudaStream_t st = kb_stream(stream);
+  kb_pool_setup();
   const kb_symfun_params& P = *h_params;
 
   if (mode == KB_SYMFUN_GENERAL)
