@@ -1,0 +1,112 @@
+"""Multi-GPU correctness check, run under torchrun on N >= 2 B200s of one box:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29511 scripts/multi_gpu_check.py
+
+1. slab decomposition with NCCL halo / reverse-force exchange == undivided computation;
+2. configuration-sharded training (NCCL gradient all-reduce) follows the single-GPU trajectory.
+Prints one JSON line from rank 0."""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+
+from kliff_b200.dataset import Configuration
+from kliff_b200.dataset.weight import Weight
+from kliff_b200.legacy import nn
+from kliff_b200.legacy.calculators import CalculatorTorch
+from kliff_b200.legacy.descriptors import SymmetryFunction
+from kliff_b200.legacy.loss import Loss
+from kliff_b200.models import NeuralNetwork
+from kliff_b200.parallel import SlabDecomposition
+
+
+def supercell(nx, ny, nz, a=5.431, sigma=0.05, seed=3):
+    basis = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0],
+                      [.25, .25, .25], [.25, .75, .75], [.75, .25, .75], [.75, .75, .25]])
+    g = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"), -1).reshape(-1, 3)
+    pos = (g[:, None, :] + basis[None]).reshape(-1, 3) * a
+    pos += np.random.default_rng(seed).normal(0, sigma, pos.shape)
+    return np.diag([a * nx, a * ny, a * nz]), pos
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    out = {"world": world}
+
+    # ---- 1. spatial decomposition over NCCL
+    cell, pos = supercell(6 * world, 3, 3)
+    n = len(pos)
+    desc = SymmetryFunction({"Si-Si": 5.0}, "cos", "set51", normalize=False, dtype=np.float64)
+    dd = SlabDecomposition(cell, [1, 1, 1], 5.0)
+    x_all = dd.wrap(torch.tensor(pos, device=dev))
+    owner = dd.owner(x_all)
+    mine = torch.nonzero(owner == rank, as_tuple=False).reshape(-1)
+    code = torch.zeros(len(mine), dtype=torch.int32, device=dev)
+    gx, gc = dd.exchange_halo(x_all[mine], code)
+    fp = dd.local_fingerprints(desc, x_all[mine], code, gx, gc)
+    w_all = torch.tensor(np.random.default_rng(0).normal(size=(n, 51)), device=dev)
+    F_own = dd.forces(w_all[mine], fp)
+    conf = Configuration(cell=cell, species=["Si"] * n, coords=pos, PBC=[True] * 3)
+    glob = desc.transform_packed([conf], device=dev)
+    F_ref = glob.forces(w_all, 0, n).reshape(n, 3)
+    errs = torch.tensor([float((fp["zeta"] - glob.zeta[mine]).abs().max() / glob.zeta.abs().max()),
+                         float((F_own - F_ref[mine]).abs().max() / F_ref.abs().max())], device=dev)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    out["slab_zeta_relerr"], out["slab_force_relerr"] = float(errs[0]), float(errs[1])
+    out["slab_local_atoms"] = int(fp["n_local"])
+    out["slab_total_atoms"] = n
+
+    # ---- 2. configuration-sharded training vs single-GPU trajectory
+    from helpers import configs_from_npz
+    every = configs_from_npz("si_varying_alat.npz", weight=Weight(forces_weight=0.3), limit=60)
+    confs = [every[i] for i in range(60) if every[i].get_num_atoms() == 64][:24]
+
+    def train(distributed):
+        d = SymmetryFunction({"Si-Si": 5.0}, "cos", "set51", normalize=True, dtype=np.float64)
+        m = NeuralNetwork(d)
+        m.add_layers(nn.Linear(51, 10), nn.Tanh(), nn.Linear(10, 10), nn.Tanh(), nn.Linear(10, 1))
+        calc = CalculatorTorch(m)
+        tmp = tempfile.mkdtemp()
+        calc.create(confs, fingerprints_filename=os.path.join(tmp, f"fp{rank}.pkl"),
+                    fingerprints_mean_stdev_filename=os.path.join(tmp, f"ms{rank}.pkl"))
+        m.set_save_metadata(prefix=os.path.join(tmp, "model"), start=1000, frequency=1000)
+        loss = Loss(calc)
+        if not distributed:
+            import kliff_b200.legacy.loss as L
+            saved = L._dist
+            L._dist = lambda: None
+            try:
+                loss.minimize(method="Adam", num_epochs=3, batch_size=8, lr=0.01)
+            finally:
+                L._dist = saved
+        else:
+            loss.minimize(method="Adam", num_epochs=3, batch_size=8, lr=0.01)
+        return np.array(loss.epoch_losses)
+
+    single = train(False)
+    multi = train(True)
+    out["dp_loss_relerr"] = float(np.max(np.abs(multi / single - 1)))
+    out["dp_losses"] = multi.tolist()
+    ok = (out["slab_zeta_relerr"] <= 1e-10 and out["slab_force_relerr"] <= 1e-10
+          and out["dp_loss_relerr"] <= 1e-9)
+    out["ok"] = bool(ok)
+    if rank == 0:
+        print(json.dumps(out))
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
