@@ -266,23 +266,40 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
     }
     __syncwarp();
 
-    // ---- phase C: pair-jk records; lanes = records --------------------------------------------
-    for (int r0 = lane; r0 < nrec; r0 += 32)
+    // ---- phase C: pair-jk records; lanes = records, two per trip so that the two dependent chains
+    //      (sqrt -> 1/r -> sincos -> 7 exp) overlap --------------------------------------------------
+    for (int r0 = lane; r0 < nrec; r0 += 64)
     {
-      const int j = PAIR[r0] & 0xff, k = PAIR[r0] >> 8;
-      const double r = sqrt(xnorm2(xsub(XYZ[k], XYZ[j]), xsub(XYZ[NP + k], XYZ[NP + j]),
-                                   xsub(XYZ[2 * NP + k], XYZ[2 * NP + j])));
-      double fc, dfc;
-      kb_cutoff_fast(r, P.rcut[SPC[j] * S + SPC[k]], fc, dfc);
-      double* rk = RK + r0 * SR;
-      const double r2 = r * r;
-      rk[0] = r; rk[1] = 1.0 / r; rk[2] = fc; rk[3] = dfc;
+      const int r1 = r0 + 32;
+      const bool two = r1 < nrec;
+      const int ja = PAIR[r0] & 0xff, ka = PAIR[r0] >> 8;
+      const int pb = two ? PAIR[r1] : PAIR[r0];
+      const int jb = pb & 0xff, kb = pb >> 8;
+      const double ra = sqrt(xnorm2(xsub(XYZ[ka], XYZ[ja]), xsub(XYZ[NP + ka], XYZ[NP + ja]),
+                                    xsub(XYZ[2 * NP + ka], XYZ[2 * NP + ja])));
+      const double rb = sqrt(xnorm2(xsub(XYZ[kb], XYZ[jb]), xsub(XYZ[NP + kb], XYZ[NP + jb]),
+                                    xsub(XYZ[2 * NP + kb], XYZ[2 * NP + jb])));
+      double fca, dfca, fcb, dfcb;
+      kb_cutoff_fast(ra, P.rcut[SPC[ja] * S + SPC[ka]], fca, dfca);
+      kb_cutoff_fast(rb, P.rcut[SPC[jb] * S + SPC[kb]], fcb, dfcb);
+      double* rka = RK + r0 * SR;
+      double* rkb = RK + (two ? r1 : r0) * SR;
+      const double r2a = ra * ra, r2b = rb * rb;
+      const double ira = 1.0 / ra, irb = 1.0 / rb;
       for (int q0 = 0; q0 < NG; q0 += 8)
       {
 #pragma unroll
         for (int u = 0; u < 8; u++)
-          if (q0 + u < NG) rk[4 + q0 + u] = kb_exp_neg(-P.grp_eta[q0 + u] * r2);
+          if (q0 + u < NG)
+          {
+            const double ea = kb_exp_neg(-P.grp_eta[q0 + u] * r2a);
+            const double eb = kb_exp_neg(-P.grp_eta[q0 + u] * r2b);
+            rka[4 + q0 + u] = ea;
+            if (two) rkb[4 + q0 + u] = eb;
+          }
       }
+      rka[0] = ra; rka[1] = ira; rka[2] = fca; rka[3] = dfca;
+      if (two) { rkb[0] = rb; rkb[1] = irb; rkb[2] = fcb; rkb[3] = dfcb; }
     }
 
     // ---- phase S: slots ordered by adjacency degree (descending, index as tie-break) ---------
@@ -473,15 +490,29 @@ int kb_symfun_warp_launch(const kb_symfun_params& P, int n_centers, const int32_
   int NP = maxn < 2 ? 2 : maxn;
   if (NP > 64) { NP = 64; *may_overflow = true; }
   NP = (NP + 1) & ~1;
-  const int worst = NP * (NP - 1) / 2;
-  // Record capacity: the number of neighbor pairs within the cutoff of each other is ~45 % of all
-  // pairs for a sphere; reserve 55 % (rounded up) unless asked for the worst case.  Atoms that
-  // exceed it are redone by the caller with full capacity.
-  int RC = full_capacity ? worst : ((worst * 11 / 20 + 15) & ~15);
-  if (RC < 64) RC = worst < 64 ? (worst > 0 ? worst : 1) : 64;
-  if (RC > worst) RC = worst > 0 ? worst : 1;
-  const size_t limit = 227 * 1024;
-  while (RC > 32 && warp_smem_bytes(P, NP, RC) > limit) RC = RC * 3 / 4;
+  const int worst = NP > 1 ? NP * (NP - 1) / 2 : 1;
+  const size_t limit = 227 * 1024, per_block_reserve = 1024;
+  // Record capacity.  Pairs of neighbors that are within the cutoff of each other are ~45 % of all
+  // pairs for a filled sphere (diamond Si at 5 A: 168 of 378).  Take the largest capacity that still
+  // lets the most warps be resident per SM, but never below 45 % of the worst case unless asked for
+  // the worst case itself; atoms that exceed it are redone by the caller with full capacity.
+  int RC = worst;
+  if (!full_capacity)
+  {
+    const size_t fixed = warp_smem_bytes(P, NP, 0);
+    const size_t per_rec = (size_t) (4 + P.n_groups) * 8 + 2;
+    const int floor_rc = (worst * 9 + 19) / 20;
+    RC = 0;
+    for (int target = 8; target >= 1 && RC == 0; target--)
+    {
+      const size_t budget = limit / target;
+      if (budget <= fixed + per_block_reserve + 32) continue;
+      long long cap = (long long) ((budget - fixed - per_block_reserve - 32) / per_rec);
+      if (cap >= floor_rc) RC = cap > worst ? worst : (int) cap;
+    }
+    if (RC == 0) RC = floor_rc;
+  }
+  while (RC > 8 && warp_smem_bytes(P, NP, RC) > limit) RC = RC * 3 / 4;
   if (RC < worst) *may_overflow = true;
   const size_t smem = warp_smem_bytes(P, NP, RC);
   if (smem > limit) return KB_OK;
@@ -494,7 +525,7 @@ int kb_symfun_warp_launch(const kb_symfun_params& P, int n_centers, const int32_
   int dev = 0, sms = 148;
   KB_CUDA(cudaGetDevice(&dev));
   KB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int per_sm = (int) ((limit + 1024) / (smem + 1024));
+  int per_sm = (int) (limit / (smem + per_block_reserve));
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;
   int grid = sms * per_sm;
