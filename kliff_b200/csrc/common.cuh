@@ -68,3 +68,22 @@ __device__ __forceinline__ double warp_sum(double v)
   for (int m = 16; m > 0; m >>= 1) v += shfl_xor_d(v, m);
   return v;
 }
+
+// Sum 32 per-lane values across the warp in 31 exchange steps (instead of 32 x 5): on return lane l
+// holds the warp-wide total of v[l].  v is clobbered.
+__device__ __forceinline__ double warp_reduce32(double (&v)[32], int lane)
+{
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1)
+  {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; i++)
+    {
+      const double keep = upper ? v[i + half] : v[i];
+      const double send = upper ? v[i] : v[i + half];
+      v[i] = keep + shfl_xor_d(send, half);
+    }
+  }
+  return v[0];
+}

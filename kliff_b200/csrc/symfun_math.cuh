@@ -83,13 +83,13 @@ __device__ __forceinline__ void kb_sincospi01(double y, double& s, double& c)
 }
 
 // cos cutoff from a precomputed 1/rc (table phases); same definition as kb_cutoff.
-__device__ __forceinline__ void kb_cutoff_fast(double r, double rc, double& fc, double& dfc)
+__device__ __forceinline__ void kb_cutoff_fast(double r, double rc, double inv_rc, double& fc, double& dfc)
 {
   double s, c;
-  kb_sincospi01(r / rc, s, c);
+  kb_sincospi01(r * inv_rc, s, c);
   const bool in = r < rc;
   fc = in ? 0.5 * (c + 1.0) : 0.0;
-  dfc = in ? -0.5 * KB_PI / rc * s : 0.0;
+  dfc = in ? (-0.5 * KB_PI) * inv_rc * s : 0.0;
 }
 
 // radial families g1/g2/g3, sym_fn.cpp:604-674.  Caller guarantees r <= rc (sym_fn.cpp:451).
@@ -99,7 +99,8 @@ __device__ __forceinline__ void kb_radial(int kind, double p0, double p1, double
   if (kind == KB_G2)
   {
     const double dr = r - p1;
-    const double e = exp(-p0 * dr * dr);
+    const double arg = -p0 * dr * dr;
+    const double e = (p0 >= 0.0) ? kb_exp_neg(arg) : exp(arg);  // uniform branch (p0 is a parameter)
     phi = e * fc;
     dphi = e * (dfc - 2.0 * p0 * dr * fc);
   }

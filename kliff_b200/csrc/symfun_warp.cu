@@ -64,7 +64,8 @@ struct WarpArgs
 __host__ __device__ inline size_t warp_smem_bytes(const kb_symfun_params& P, int NP, int RC)
 {
   const int NG = P.n_groups, NT = P.n_two;
-  size_t d = (size_t) 3 * NP + (size_t) NP * (8 + NG) + (size_t) RC * (4 + NG) + SC_DOUBLES + 4 * (size_t) NT;
+  size_t d = (size_t) 3 * NP + (size_t) NP * (8 + NG) + (size_t) RC * (4 + NG) + SC_DOUBLES + 4 * (size_t) NT
+             + KB_MAX_SPECIES * KB_MAX_SPECIES;
   size_t bytes = d * 8 + (size_t) NP * 8;        // + adjacency masks
   bytes += (size_t) NP * 8;                      // species, record base
   bytes += (size_t) (NP * NP + RC) * 2;          // per-slot record lists, pair list
@@ -88,7 +89,8 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
   double* RK = TJ + NP * SJ;                          // [RC][SR]: r 1/r fc dfc x_g..
   double* SC = RK + RC * SR;                          // [32][SCW]
   double* Z2 = SC + SC_DOUBLES;                       // [NT] radial zeta, [3 NT] radial centre slot
-  unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(Z2 + 4 * NT);  // [NP]
+  double* RCI = Z2 + 4 * NT;                          // [S][S] 1 / rc
+  unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(RCI + KB_MAX_SPECIES * KB_MAX_SPECIES);  // [NP]
   int* SPC = reinterpret_cast<int*>(ADJ + NP);        // [NP]
   int* BASE = SPC + NP;                               // [NP] first record slot of row j (pairs j<k)
   unsigned short* JR = reinterpret_cast<unsigned short*>(BASE + NP);   // [NP][NP] record of (slot, idx)
@@ -112,6 +114,8 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
     for (int e = 0; e < GW; e++) gout[e] = P.grp_out[g][e];
   }
   const double p2tab[GW] = {1.0, 1.0, 0.5, 0.5, 0.125, 0.125, 1.0 / 32768.0, 1.0 / 32768.0};
+  for (int q = lane; q < S * S; q += 32) RCI[q] = 1.0 / P.rcut[q];
+  __syncwarp();
 
   for (;;)
   {
@@ -151,17 +155,18 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
         const int sj = A.species[j];
         const double xj = A.coords[3 * j], yj = A.coords[3 * j + 1], zj = A.coords[3 * j + 2];
         const double vx = xsub(xj, xi), vy = xsub(yj, yi), vz = xsub(zj, zi);
-        r = sqrt(xnorm2(vx, vy, vz));   // sym_fn.cpp:447-448
+        const double r2x = xnorm2(vx, vy, vz);
+        r = sqrt(r2x);                  // sym_fn.cpp:447-448
         const double rc = P.rcut[si * S + sj];
         act = !(r > rc);                // :451
-        const double ir = 1.0 / r;
-        kb_cutoff_fast(r, rc, fc, dfc);
+        const double ir = rsqrt(r2x);   // independent of the sqrt chain
+        kb_cutoff_fast(r, rc, RCI[si * S + sj], fc, dfc);
         if (!act) { fc = 0.0; dfc = 0.0; }
         ux = vx * ir; uy = vy * ir; uz = vz * ir;
         XYZ[jj] = xj; XYZ[NP + jj] = yj; XYZ[2 * NP + jj] = zj;
         SPC[jj] = sj;
         double* tj = TJ + jj * SJ;
-        const double r2 = r * r;
+        const double r2 = r2x;
         tj[0] = r; tj[1] = r2; tj[2] = ir; tj[3] = fc; tj[4] = dfc; tj[5] = ux; tj[6] = uy; tj[7] = uz;
         for (int q0 = 0; q0 < NG; q0 += 8)
         {
@@ -171,23 +176,29 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
         }
       }
       ACT |= (unsigned long long) __ballot_sync(FULL, act) << j0;
-      for (int q = 0; q < NT; q++)
+      for (int q0 = 0; q0 < NT; q0 += 8)
       {
-        double phi = 0.0, dphi = 0.0;
-        if (act) kb_radial(P.two_kind[q], P.two_p0[q], P.two_p1[q], r, fc, dfc, phi, dphi);
-        const double px = dphi * ux, py = dphi * uy, pz = dphi * uz;  // :497
-        if (GRAD && jj < n)
+        double v[32];
+#pragma unroll
+        for (int u = 0; u < 8; u++)  // 8 independent radial sets per trip
         {
-          double* o = blk + (int64_t) P.two_out[q] * row + 3 * jj;
-          o[0] = px; o[1] = py; o[2] = pz;
+          const int q = q0 + u;
+          double phi = 0.0, dphi = 0.0;
+          if (q < NT && act) kb_radial(P.two_kind[q], P.two_p0[q], P.two_p1[q], r, fc, dfc, phi, dphi);
+          const double px = dphi * ux, py = dphi * uy, pz = dphi * uz;  // :497
+          if (GRAD && q < NT && jj < n)
+          {
+            double* o = blk + (int64_t) P.two_out[q] * row + 3 * jj;
+            o[0] = px; o[1] = py; o[2] = pz;
+          }
+          v[4 * u] = phi; v[4 * u + 1] = px; v[4 * u + 2] = py; v[4 * u + 3] = pz;
         }
-        const double s0 = warp_sum(phi);
-        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        if (GRAD) { s1 = warp_sum(px); s2 = warp_sum(py); s3 = warp_sum(pz); }
-        if (lane == 0)
+        const double tot = warp_reduce32(v, lane);  // lane l: total of value (set l/4, component l%4)
+        const int q = q0 + (lane >> 2), comp = lane & 3;
+        if (q < NT)
         {
-          Z2[q] += s0;
-          Z2[NT + 3 * q] += s1; Z2[NT + 3 * q + 1] += s2; Z2[NT + 3 * q + 2] += s3;
+          if (comp == 0) Z2[q] += tot;
+          else Z2[NT + 3 * q + comp - 1] += tot;
         }
       }
     }
@@ -275,17 +286,18 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       const int ja = PAIR[r0] & 0xff, ka = PAIR[r0] >> 8;
       const int pb = two ? PAIR[r1] : PAIR[r0];
       const int jb = pb & 0xff, kb = pb >> 8;
-      const double ra = sqrt(xnorm2(xsub(XYZ[ka], XYZ[ja]), xsub(XYZ[NP + ka], XYZ[NP + ja]),
-                                    xsub(XYZ[2 * NP + ka], XYZ[2 * NP + ja])));
-      const double rb = sqrt(xnorm2(xsub(XYZ[kb], XYZ[jb]), xsub(XYZ[NP + kb], XYZ[NP + jb]),
-                                    xsub(XYZ[2 * NP + kb], XYZ[2 * NP + jb])));
+      const double r2a = xnorm2(xsub(XYZ[ka], XYZ[ja]), xsub(XYZ[NP + ka], XYZ[NP + ja]),
+                                xsub(XYZ[2 * NP + ka], XYZ[2 * NP + ja]));
+      const double r2b = xnorm2(xsub(XYZ[kb], XYZ[jb]), xsub(XYZ[NP + kb], XYZ[NP + jb]),
+                                xsub(XYZ[2 * NP + kb], XYZ[2 * NP + jb]));
+      const double ra = sqrt(r2a), rb = sqrt(r2b);
+      const double ira = rsqrt(r2a), irb = rsqrt(r2b);
       double fca, dfca, fcb, dfcb;
-      kb_cutoff_fast(ra, P.rcut[SPC[ja] * S + SPC[ka]], fca, dfca);
-      kb_cutoff_fast(rb, P.rcut[SPC[jb] * S + SPC[kb]], fcb, dfcb);
+      const int pa = SPC[ja] * S + SPC[ka], pb2 = SPC[jb] * S + SPC[kb];
+      kb_cutoff_fast(ra, P.rcut[pa], RCI[pa], fca, dfca);
+      kb_cutoff_fast(rb, P.rcut[pb2], RCI[pb2], fcb, dfcb);
       double* rka = RK + r0 * SR;
       double* rkb = RK + (two ? r1 : r0) * SR;
-      const double r2a = ra * ra, r2b = rb * rb;
-      const double ira = 1.0 / ra, irb = 1.0 / rb;
       for (int q0 = 0; q0 < NG; q0 += 8)
       {
 #pragma unroll
