@@ -28,6 +28,9 @@ if ROOT not in sys.path:
 A_SI, SIGMA, RC = 5.431, 0.05, 5.0
 FLOP_CANON = 380618.0   # per atom, set51 / n=28 / T=378 / T4=168
 BYTES_CANON = 36724.0   # per atom, fp64 zeta + dG/dr written + inputs read once
+# dram__bytes_read.sum + dram__bytes_write.sum of symfun_warp_kernel<true> on this very workload
+# (1 000 000 atoms, one launch), ncu --set full capture of round 1: profiles/r01_ncu_symfun_warp_1M_traffic.txt
+TRAFFIC_NCU_BYTES_PER_ATOM = 48855.0
 
 
 def diamond(nx, seed):
@@ -348,7 +351,9 @@ def main():
                    "step_breakdown_ms": {"paddings+neighbors": float(np.mean(nl_ms)),
                                          "symfun+dG/dr": float(np.mean(sym_ms))}},
         "roofline": {"kernel": "symfun_warp_kernel<true>", "bound": "hbm", "achieved": ach_gbs,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                     "traffic": TRAFFIC_NCU_BYTES_PER_ATOM * n if args.nx == 50 else None,
+                     "traffic_source": "ncu capture profiles/r01_ncu_symfun_warp_1M_traffic.txt (bytes per launch)",
                      "peak_source": peak_src,
                      "note": "algorithmic bytes 36 724 B/atom; the kernel is FP64-pipe bound, see roofline_fp64"},
         "roofline_fp64": {"kernel": "symfun_warp_kernel<true>", "bound": "fp64", "achieved": ach_tf,
