@@ -194,6 +194,65 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def train_epoch_probe(ncfg, dev):
+    """Second half of BASELINE.json's metric ("train epoch time"): synthetic set of `ncfg` 64-atom
+    diamond-Si configurations (2x2x2 cells, a ~ U(5.2, 5.7), jitter 0.1 A, seed = index; reference
+    energies/forces = N(0,1) noise), set51, MLP 51-10-10-1, Adam lr 1e-3, batch 100, fp32 model as in
+    the reference's tutorials.  Reports create() (descriptors + dG/dr + normalisation) and the time
+    of one optimisation pass over the set through Loss.minimize."""
+    import contextlib
+    import io
+    import tempfile
+
+    import torch
+
+    from kliff_b200.dataset import Configuration
+    from kliff_b200.dataset.weight import Weight
+    from kliff_b200.legacy import nn
+    from kliff_b200.legacy.calculators import CalculatorTorch
+    from kliff_b200.legacy.descriptors import SymmetryFunction
+    from kliff_b200.legacy.loss import Loss
+    from kliff_b200.models import NeuralNetwork
+
+    basis = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0],
+                      [.25, .25, .25], [.25, .75, .75], [.75, .25, .75], [.75, .75, .25]])
+    g = np.stack(np.meshgrid(np.arange(2), np.arange(2), np.arange(2), indexing="ij"), -1).reshape(-1, 3)
+    frac = (g[:, None, :] + basis[None]).reshape(-1, 3)
+    weight = Weight(forces_weight=0.3)
+    confs = []
+    for c in range(ncfg):
+        rng = np.random.default_rng(c)
+        a = rng.uniform(5.2, 5.7)
+        pos = frac * a + rng.normal(0, 0.1, frac.shape)
+        confs.append(Configuration(cell=np.eye(3) * 2 * a, species=["Si"] * 64, coords=pos, PBC=[True] * 3,
+                                   energy=float(rng.normal()), forces=rng.normal(size=(64, 3)),
+                                   weight=weight, identifier=f"syn{c}"))
+    desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": RC}, hyperparams="set51", normalize=True)
+    desc.store_gradients_on_disk = False  # GPU-resident gradients only; the pickle keeps zeta/energy/forces
+    model = NeuralNetwork(desc)
+    model.add_layers(nn.Linear(51, 10), nn.Tanh(), nn.Linear(10, 10), nn.Tanh(), nn.Linear(10, 1))
+    tmp = tempfile.mkdtemp()
+    model.set_save_metadata(prefix=os.path.join(tmp, "m"), start=10 ** 9, frequency=10 ** 9)
+    calc = CalculatorTorch(model)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    calc.create(confs, fingerprints_filename=os.path.join(tmp, "fp.pkl"),
+                fingerprints_mean_stdev_filename=os.path.join(tmp, "ms.pkl"))
+    torch.cuda.synchronize()
+    t_create = time.time() - t0
+    loss = Loss(calc)
+    with contextlib.redirect_stdout(io.StringIO()):
+        loss.minimize(method="Adam", num_epochs=1, batch_size=100, lr=1e-3)  # warm-up epoch (+ final pass)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        loss.minimize(method="Adam", num_epochs=2, batch_size=100, lr=1e-3)
+        torch.cuda.synchronize()
+        t_three = time.time() - t0  # 2 optimisation epochs + the final loss pass
+    return {"configs": ncfg, "atoms": 64 * ncfg, "create_s": t_create,
+            "epoch_s": t_three / 3.0, "steps_per_epoch": (ncfg + 99) // 100,
+            "note": "epoch_s = (2 Adam epochs + final loss pass) / 3, batch 100, fp32 MLP, fp64 dG/dr"}
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -203,6 +262,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=50, help="conventional cells per edge (50 -> 1M atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--epoch-configs", type=int, default=1000,
+                    help="size of the synthetic 64-atom-configuration set for the train_epoch probe (0 = off)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -367,6 +428,11 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if args.epoch_configs > 0:
+        try:
+            line["train_epoch"] = train_epoch_probe(args.epoch_configs, dev)
+        except Exception as e:  # reported, never required
+            line["train_epoch"] = {"error": str(e)}
     if not args.no_cpu_baseline:
         try:
             base = CpuBaseline(nx=12)
