@@ -10,35 +10,51 @@
 // 40 % of warp time sat in CTA barriers between the table / record / triple / copy phases, lanes were
 // 74 % utilised, and every eta-lane recomputed the triple geometry.  Here ONE WARP owns an atom end
 // to end — no __syncthreads, only __syncwarp — and 8 such warps are resident per SM, each with its
-// own ~25 KB of shared memory, so one warp's transcendental-heavy table phases overlap another
-// warp's FMA-bound triple loop on the same FP64 pipe.
+// own ~22 KB of shared memory, so one warp's latency-bound table phases overlap another warp's
+// FMA-bound triple loop on the same FP64 pipe.
 //
 // Per atom:
-//   A  pair-ij table   lanes = neighbors: r, 1/r, unit vector, fc, fc', exp(-eta_g r^2) per eta   [smem]
-//   D  radial sets     lanes = neighbors: phi, dphi -> rows written straight to global
-//   B  pair-jk test    row j, lanes = k>j: reference predicate r_jk <= rc_jk (sym_fn.cpp:729), ballot
-//                      compaction into record slots + a 64-bit adjacency mask per neighbor (no atomics:
-//                      the warp is the only writer)
-//   C  pair-jk records lanes = records: r, 1/r, fc, fc', exp(-eta_g r^2)                             [smem]
+//   A  pair-ij table   lanes = neighbors: r, r^2, 1/r, unit vector, fc, fc'                         [smem]
+//   D  radial sets     lanes = neighbors, 8 sets at a time: phi, dphi -> rows written straight to
+//                      global; zeta and centre slot by a 31-step transpose reduction
+//   B  pair-jk test    lane = row j computes its whole 64-bit adjacency row in registers with the
+//                      reference predicate r_jk <= rc_jk (sym_fn.cpp:729); record slots from a warp scan;
+//                      per-slot neighbor / record lists (no ballots, no atomics)
+//   C  pair-jk records lanes = records (two per trip): r, 1/r, fc, fc'                               [smem]
 //   S  slots sorted by adjacency degree, so that the 32/NGP slots sharing a warp-item have the same
 //      trip count (diamond Si: degrees 18/12/10 -> zero divergence)
 //   E  triple loop     item = (slot k, eta-group g), lane = (k_sub, g).  Each step, the NGP lanes of a
-//      slot first compute the geometry of NGP ordered pairs (j -> k) ONCE (cos, F, and the three
-//      3-vectors W1, P, R) into a 3 KB scratch, then every eta-lane sweeps those entries with a
+//      slot first compute, ONCE per ordered pair (j -> k): cos, F, sum of squared distances, the three
+//      3-vectors W1, P, R and the power chain (1 +- cos)^{1,2,4,16} with its derivative factors, into a
+//      bank-padded scratch (28 doubles per pair); then every eta-lane sweeps those entries with one
+//      exponential E_g = e^{-eta_g (rij^2+rik^2+rjk^2)} (Estrin polynomial, dependency depth 5) and a
 //      rank-2 update of its 8x3 register accumulators:
-//            acc[e][c] += C'_e(cos) * (e_g F W1[c]) + C_e(cos) * (E_g (eta_g P[c] + R[c]))
-//      (2 DFMA per entry-component; powers of (1 +- cos) by a multiplication chain).
+//            acc[e][c] += C'_e * (E_g F W1[c]) + C_e * (E_g (eta_g P[c] + R[c]))
 //      Only the derivative w.r.t. slot k is accumulated, so there are no write conflicts; every
 //      unordered triple is visited from both ends like the reference's slots jj/kk (:587-593).
+//      (An earlier revision tabulated e^{-eta_g r^2} per pair in shared memory; dropping those tables
+//      removed 1 372 exponentials per atom from the table phases and 10 KB of shared memory per warp
+//      for one Estrin exponential per sweep step — measured 10.1 -> 9.4 ms on 216 k atoms.)
 //   F  centre slot = -sum_k slot_k (translation invariance) and zeta = 1/2 sum over ordered pairs are
 //      carried in registers across items and reduced once per atom with xor-shuffles.
 #include "common.cuh"
 #include "symfun_math.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int GW = KB_GROUP_WIDTH;
-constexpr int SCW = 12;  // doubles per scratch entry
+// resident warps per SM the kernel is compiled for: the gradient variant needs ~232 registers (8x3
+// accumulators + 8x3 centre partial sums per lane) and spilling them costs more than the extra
+// warps give (measured: 10 -> 11.4 ms vs 8 -> 9.4 ms on 216k atoms); the value-only variant fits 12.
+#ifndef KB_WARP_MIN_BLOCKS
+#define KB_WARP_MIN_BLOCKS 8
+#endif
+#ifndef KB_WARP_MIN_BLOCKS_NOGRAD
+#define KB_WARP_MIN_BLOCKS_NOGRAD 12
+#endif
+constexpr int SCW = 28;  // doubles per scratch entry: 12 geometry + 8 C + 8 C'
 // scratch: 32 entries; each group of NGP entries is followed by 2 doubles of padding so that the
 // 32/NGP groups, which are read simultaneously (broadcast inside a group), fall on different banks
 constexpr int SC_DOUBLES = 32 * SCW + 2 * 32;
@@ -64,8 +80,8 @@ struct WarpArgs
 __host__ __device__ inline size_t warp_smem_bytes(const kb_symfun_params& P, int NP, int RC)
 {
   const int NG = P.n_groups, NT = P.n_two;
-  size_t d = (size_t) 3 * NP + (size_t) NP * (8 + NG) + (size_t) RC * (4 + NG) + SC_DOUBLES + 4 * (size_t) NT
-             + KB_MAX_SPECIES * KB_MAX_SPECIES;
+  size_t d = (size_t) 3 * NP + (size_t) NP * 8 + (size_t) RC * 4 + SC_DOUBLES + 4 * (size_t) NT
+             + (size_t) P.n_species * P.n_species;
   size_t bytes = d * 8 + (size_t) NP * 8;        // + adjacency masks
   bytes += (size_t) NP * 8;                      // species, record base
   bytes += (size_t) (NP * NP + RC) * 2;          // per-slot record lists, pair list
@@ -74,14 +90,14 @@ __host__ __device__ inline size_t warp_smem_bytes(const kb_symfun_params& P, int
 }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(32, 8)
+__global__ void __launch_bounds__(32, GRAD ? KB_WARP_MIN_BLOCKS : KB_WARP_MIN_BLOCKS_NOGRAD)
 symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x;
   const unsigned FULL = 0xffffffffu;
   const int NP = A.NP, RC = A.RC, NG = P.n_groups, NGP = A.NGP, D = P.n_desc, NT = P.n_two;
-  const int SJ = 8 + NG, SR = 4 + NG;
+  constexpr int SJ = 8, SR = 4;
   const int S = P.n_species;
 
   double* XYZ = reinterpret_cast<double*>(smem_raw);  // [3][NP]
@@ -90,7 +106,7 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
   double* SC = RK + RC * SR;                          // [32][SCW]
   double* Z2 = SC + SC_DOUBLES;                       // [NT] radial zeta, [3 NT] radial centre slot
   double* RCI = Z2 + 4 * NT;                          // [S][S] 1 / rc
-  unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(RCI + KB_MAX_SPECIES * KB_MAX_SPECIES);  // [NP]
+  unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(RCI + S * S);  // [NP]
   int* SPC = reinterpret_cast<int*>(ADJ + NP);        // [NP]
   int* BASE = SPC + NP;                               // [NP] first record slot of row j (pairs j<k)
   unsigned short* JR = reinterpret_cast<unsigned short*>(BASE + NP);   // [NP][NP] record of (slot, idx)
@@ -168,12 +184,6 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
         double* tj = TJ + jj * SJ;
         const double r2 = r2x;
         tj[0] = r; tj[1] = r2; tj[2] = ir; tj[3] = fc; tj[4] = dfc; tj[5] = ux; tj[6] = uy; tj[7] = uz;
-        for (int q0 = 0; q0 < NG; q0 += 8)
-        {
-#pragma unroll
-          for (int u = 0; u < 8; u++)  // independent exponentials: let them overlap
-            if (q0 + u < NG) tj[8 + q0 + u] = act ? kb_exp_neg(-P.grp_eta[q0 + u] * r2) : 0.0;
-        }
       }
       ACT |= (unsigned long long) __ballot_sync(FULL, act) << j0;
       for (int q0 = 0; q0 < NT; q0 += 8)
@@ -298,18 +308,6 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       kb_cutoff_fast(rb, P.rcut[pb2], RCI[pb2], fcb, dfcb);
       double* rka = RK + r0 * SR;
       double* rkb = RK + (two ? r1 : r0) * SR;
-      for (int q0 = 0; q0 < NG; q0 += 8)
-      {
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-          if (q0 + u < NG)
-          {
-            const double ea = kb_exp_neg(-P.grp_eta[q0 + u] * r2a);
-            const double eb = kb_exp_neg(-P.grp_eta[q0 + u] * r2b);
-            rka[4 + q0 + u] = ea;
-            if (two) rkb[4 + q0 + u] = eb;
-          }
-      }
       rka[0] = ra; rka[1] = ira; rka[2] = fca; rka[3] = dfca;
       if (two) { rkb[0] = rb; rkb[1] = irb; rkb[2] = fcb; rkb[3] = dfcb; }
     }
@@ -339,7 +337,6 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       const double rik = tk[0], rik2 = tk[1], irik = tk[2], fik = tk[3], dfik = tk[4];
       const double ukx = tk[5], uky = tk[6], ukz = tk[7];
       const double xk = XYZ[k], yk = XYZ[NP + k], zk = XYZ[2 * NP + k];
-      const double xik = valid_g ? tk[8 + g] : 0.0;
       const int degk = valid_k ? DEG[k] : 0;
       const int maxdeg = __reduce_max_sync(FULL, degk);
       const unsigned char* jl = JL + k * NP;
@@ -378,7 +375,23 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
           sc[2] = dct_ik * ukx + dct_jk * wx; sc[3] = dct_ik * uky + dct_jk * wy; sc[4] = dct_ik * ukz + dct_jk * wz;
           sc[5] = a * ukx + b * wx;           sc[6] = a * uky + b * wy;           sc[7] = a * ukz + b * wz;
           sc[8] = dF_ik * ukx + dF_jk * wx;   sc[9] = dF_ik * uky + dF_jk * wy;   sc[10] = dF_ik * ukz + dF_jk * wz;
-          sc[11] = __hiloint2double(rec, j);
+          sc[11] = rij2 + rik2 + rjk2;
+          // (1 + lambda cos)^zeta and its derivative factor for zeta in {1,2,4,16}, lambda = -1, +1:
+          // entries e = 2*zi + si (sym_fn.cpp:749-767, multiplication chain instead of pow)
+#pragma unroll
+          for (int si2 = 0; si2 < 2; si2++)
+          {
+            const double lam = si2 ? 1.0 : -1.0;
+            double bse = fma(lam, ct, 1.0);
+            const bool ok = bse > 0.0;  // guard of :755-767
+            bse = ok ? bse : 0.0;
+            const double b2 = bse * bse, b3 = b2 * bse, b4 = b2 * b2, b8 = b4 * b4;
+            const double b16 = b8 * b8, b15 = b8 * b4 * b3;
+            sc[12 + 0 + si2] = bse; sc[20 + 0 + si2] = ok ? lam : 0.0;
+            sc[12 + 2 + si2] = b2;  sc[20 + 2 + si2] = 2.0 * lam * bse;
+            sc[12 + 4 + si2] = b4;  sc[20 + 4 + si2] = 4.0 * lam * b3;
+            sc[12 + 6 + si2] = b16; sc[20 + 6 + si2] = 16.0 * lam * b15;
+          }
         }
         const int left = degk - s0;
         const int cnt = left < 0 ? 0 : (left < NGP ? left : NGP);
@@ -391,26 +404,18 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
           {
             const double* sc = scg + ej * SCW;
             const double ct = sc[0], F = sc[1];
-            const int j = __double2loint(sc[11]), rec = __double2hiint(sc[11]);
-            const double E = TJ[j * SJ + 8 + g] * xik * RK[rec * SR + 4 + g];
+            const double E = kb_exp_neg(-eta * sc[11]);  // e^{-eta (rij^2 + rik^2 + rjk^2)}, :770
             const double eF = E * F, Ee = E * eta;
             const double v1x = eF * sc[2], v1y = eF * sc[3], v1z = eF * sc[4];
             const double v2x = fma(Ee, sc[5], E * sc[8]), v2y = fma(Ee, sc[6], E * sc[9]),
                          v2z = fma(Ee, sc[7], E * sc[10]);
             double C[GW], Cp[GW];
 #pragma unroll
-            for (int s = 0; s < 2; s++)
+            for (int e = 0; e < GW; e += 2)
             {
-              const double lam = s ? 1.0 : -1.0;
-              double bse = fma(lam, ct, 1.0);
-              const bool ok = bse > 0.0;  // guard of :755-767
-              bse = ok ? bse : 0.0;
-              const double b2 = bse * bse, b3 = b2 * bse, b4 = b2 * b2, b8 = b4 * b4;
-              const double b16 = b8 * b8, b15 = b8 * b4 * b3;
-              C[0 + s] = bse; Cp[0 + s] = ok ? lam : 0.0;
-              C[2 + s] = b2;  Cp[2 + s] = 2.0 * lam * bse;
-              C[4 + s] = b4;  Cp[4 + s] = 4.0 * lam * b3;
-              C[6 + s] = b16; Cp[6 + s] = 16.0 * lam * b15;
+              const double2 c2 = *reinterpret_cast<const double2*>(sc + 12 + e);
+              const double2 d2 = *reinterpret_cast<const double2*>(sc + 20 + e);
+              C[e] = c2.x; C[e + 1] = c2.y; Cp[e] = d2.x; Cp[e + 1] = d2.y;
             }
 #pragma unroll
             for (int e = 0; e < GW; e++)
@@ -512,10 +517,11 @@ int kb_symfun_warp_launch(const kb_symfun_params& P, int n_centers, const int32_
   if (!full_capacity)
   {
     const size_t fixed = warp_smem_bytes(P, NP, 0);
-    const size_t per_rec = (size_t) (4 + P.n_groups) * 8 + 2;
+    const size_t per_rec = (size_t) 4 * 8 + 2;
     const int floor_rc = (worst * 9 + 19) / 20;
     RC = 0;
-    for (int target = 8; target >= 1 && RC == 0; target--)
+    const int want_blocks = d_dz != nullptr ? KB_WARP_MIN_BLOCKS : KB_WARP_MIN_BLOCKS_NOGRAD;
+    for (int target = want_blocks; target >= 1 && RC == 0; target--)
     {
       const size_t budget = limit / target;
       if (budget <= fixed + per_block_reserve + 32) continue;
@@ -538,7 +544,13 @@ int kb_symfun_warp_launch(const kb_symfun_params& P, int n_centers, const int32_
   KB_CUDA(cudaGetDevice(&dev));
   KB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int per_sm = (int) (limit / (smem + per_block_reserve));
-  if (per_sm > 8) per_sm = 8;
+  const int max_blocks = d_dz != nullptr ? KB_WARP_MIN_BLOCKS : KB_WARP_MIN_BLOCKS_NOGRAD;
+  if (per_sm > max_blocks) per_sm = max_blocks;
+  if (const char* cap = getenv("KB_WARPS_PER_SM"))  // tuning experiments only
+  {
+    const int c = atoi(cap);
+    if (c >= 1 && c < per_sm) per_sm = c;
+  }
   if (per_sm < 1) per_sm = 1;
   int grid = sms * per_sm;
   if (grid > n_centers) grid = n_centers;
