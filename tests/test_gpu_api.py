@@ -285,3 +285,23 @@ def test_custom_residual_function_route(workdir):
     loss = Loss(calc, residual_fn=energy_residual, residual_data={"normalize_by_natoms": False})
     loss.minimize(method="Adam", num_epochs=3, batch_size=2, lr=0.01)
     assert len(loss.epoch_losses) == 4 and loss.epoch_losses[-1] < loss.epoch_losses[0]
+
+
+def test_new_api_descriptor_forward_backward():
+    """tests/transformations/test_descriptors.py:14-72 of the reference: new-API Descriptor.forward
+    equals the legacy zeta, backward(ones) equals tensordot(ones, dzetadr) (set30 and set51, rc 4.5)."""
+    from kliff_b200.transforms.configuration_transforms import (Descriptor, symmetry_functions_set30,
+                                                                symmetry_functions_set51)
+    config = configs_from_npz("si_varying_alat.npz", limit=8)[7]
+    for hp in (symmetry_functions_set30(), symmetry_functions_set51()):
+        old = SymmetryFunction(cut_dists={"Si-Si": 4.5}, cut_name="cos", hyperparams=hp, normalize=False)
+        z_old, dz_old, _ = old.transform(config, fit_forces=True, fit_stress=False)
+        new = Descriptor(cutoff=4.5, species=["Si"], descriptor="SymmetryFunctions", hyperparameters=hp)
+        z_new = new.forward(config)
+        assert np.allclose(z_old, z_new)
+        vjp_new = new.backward(config, np.ones_like(z_new))
+        vjp_old = np.tensordot(np.ones_like(z_old), dz_old, ([0, 1], [0, 1])).reshape(-1, 3)
+        assert np.allclose(vjp_old, vjp_new, rtol=1e-9, atol=1e-10 * np.abs(dz_old).max())
+    state = new(config, return_extended_state=True)
+    assert state["n_atoms"] == 64 and state["descriptor"].shape == (64, 51)
+    assert state["num_neigh"].shape == (64,) and state["neigh_list"].shape[0] == state["num_neigh"].sum()
