@@ -138,6 +138,12 @@ void kb_nl_destroy(kb_nl_plan* plan, void* stream);
 /* [D][n+1][3] (slot n = centre atom, sym_fn.hpp:188-191) stored at d_dz + d_dz_ptr[t].        */
 /* d_dz_ptr comes from kb_symfun_block_offsets: blocks are padded to 16 doubles (128 B).       */
 /* ------------------------------------------------------------------------------------------ */
+/* Storage type of the packed dG/dr blocks.  Arithmetic is always fp64; KB_F32 rounds the finished
+ * block to float on the way out (what the reference does with its default dtype=np.float32,
+ * kliff/legacy/descriptors/descriptor.py:197-205) and halves HBM footprint and contraction traffic. */
+#define KB_F64 0
+#define KB_F32 1
+
 #define KB_SYMFUN_AUTO 0
 #define KB_SYMFUN_GENERAL 1     /* global-atomics kernel: any neighbor count */
 #define KB_SYMFUN_TILED 2       /* CTA-per-atom shared-memory kernel: n <= 64, any families */
@@ -149,8 +155,8 @@ int kb_symfun_block_offsets(int32_t n_centers, const int32_t* d_centers,
 int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_centers,
                       const int32_t* d_centers, const double* d_coords, const int32_t* d_species,
                       const int64_t* d_nl_offsets, const int32_t* d_nl_indices, int32_t maxn,
-                      double* d_zeta, double* d_dz, const int64_t* d_dz_ptr, int32_t mode,
-                      void* stream);
+                      double* d_zeta, void* d_dz, int32_t dz_dtype, const int64_t* d_dz_ptr,
+                      int32_t mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Chain-rule force assembly — replaces CalculatorTorch._compute_forces on the dense           */
@@ -164,12 +170,12 @@ int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_centers,
 /* ------------------------------------------------------------------------------------------ */
 int kb_force_scatter_fwd(int32_t n_centers, const int32_t* d_centers, const int64_t* d_nl_offsets,
                          const int32_t* d_nl_indices, const int32_t* d_image, int32_t n_desc,
-                         const double* d_dEdG, const double* d_scale, const double* d_dz,
-                         const int64_t* d_dz_ptr, double* d_forces, void* stream);
+                         const double* d_dEdG, const double* d_scale, const void* d_dz,
+                         int32_t dz_dtype, const int64_t* d_dz_ptr, double* d_forces, void* stream);
 int kb_force_scatter_bwd(int32_t n_centers, const int32_t* d_centers, const int64_t* d_nl_offsets,
                          const int32_t* d_nl_indices, const int32_t* d_image, int32_t n_desc,
-                         const double* d_gF, const double* d_scale, const double* d_dz,
-                         const int64_t* d_dz_ptr, double* d_gdEdG, void* stream);
+                         const double* d_gF, const double* d_scale, const void* d_dz,
+                         int32_t dz_dtype, const int64_t* d_dz_ptr, double* d_gdEdG, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Dense views for small configurations — what SymmetryFunction.transform returns             */
@@ -178,8 +184,9 @@ int kb_force_scatter_bwd(int32_t n_centers, const int32_t* d_centers, const int6
 /* ------------------------------------------------------------------------------------------ */
 int kb_dense_fold(int32_t n_centers, const int32_t* d_centers, const int64_t* d_nl_offsets,
                   const int32_t* d_nl_indices, const int32_t* d_image, const double* d_coords,
-                  int32_t n_desc, int32_t n_contrib, const double* d_dz, const int64_t* d_dz_ptr,
-                  double* d_dense_forces, double* d_dense_stress, void* stream);
+                  int32_t n_desc, int32_t n_contrib, const void* d_dz, int32_t dz_dtype,
+                  const int64_t* d_dz_ptr, double* d_dense_forces, double* d_dense_stress,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Measurement helpers (bench.py): FP64 FMA peak of this device, TFLOP/s (2 flops per FMA),    */

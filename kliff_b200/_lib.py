@@ -14,6 +14,7 @@ KB_GROUP_WIDTH = 8
 
 KB_OK, KB_ERR_REFERENCE, KB_ERR_INVALID, KB_ERR_LIMIT, KB_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 KB_SYMFUN_AUTO, KB_SYMFUN_GENERAL, KB_SYMFUN_TILED, KB_SYMFUN_WARP = 0, 1, 2, 3
+KB_F64, KB_F32 = 0, 1
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libkliff_b200.so")
 
@@ -89,10 +90,10 @@ def lib():
     L.kb_nl_destroy.restype = None
     L.kb_symfun_block_offsets.argtypes = [i32, vp, vp, i32, vp, C.POINTER(i64), vp]
     L.kb_symfun_forward.argtypes = [C.POINTER(kb_symfun_params), i32, vp, vp, vp, vp, vp, i32, vp,
-                                    vp, vp, i32, vp]
-    L.kb_force_scatter_fwd.argtypes = [i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
-    L.kb_force_scatter_bwd.argtypes = [i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
-    L.kb_dense_fold.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
+                                    vp, i32, vp, i32, vp]
+    L.kb_force_scatter_fwd.argtypes = [i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp]
+    L.kb_force_scatter_bwd.argtypes = [i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp]
+    L.kb_dense_fold.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, vp, vp, vp]
     L.kb_probe_fp64_peak.argtypes = [C.POINTER(dbl), vp]
     L.kb_probe_hbm_copy.argtypes = [C.c_size_t, C.POINTER(dbl), vp]
     L.kb_launch_count.argtypes = [i32]

@@ -14,12 +14,12 @@ namespace {
 constexpr int SC_WARPS = 8;
 constexpr int SC_COLS = 4;  // columns per lane per pass -> 128 columns (n <= 41) in one pass
 
-template <bool BWD>
+template <bool BWD, typename TDz>
 __global__ void __launch_bounds__(SC_WARPS * 32)
 force_scatter_kernel(int n_centers, const int32_t* __restrict__ centers,
                      const int64_t* __restrict__ nl_off, const int32_t* __restrict__ nl_idx,
                      const int32_t* __restrict__ image, int D, const double* __restrict__ vec_in,
-                     const double* __restrict__ scale, const double* __restrict__ dz,
+                     const double* __restrict__ scale, const TDz* __restrict__ dz,
                      const int64_t* __restrict__ dz_ptr, double* __restrict__ out)
 {
   extern __shared__ double wsm[];  // fwd: [SC_WARPS][D] weights
@@ -30,7 +30,7 @@ force_scatter_kernel(int n_centers, const int32_t* __restrict__ centers,
   const int64_t off = nl_off[a];
   const int n = (int) (nl_off[a + 1] - off);
   const int row = 3 * (n + 1);
-  const double* blk = dz + dz_ptr[t];
+  const TDz* blk = dz + dz_ptr[t];
   double* w = wsm + warp * D;
   if (!BWD)
   {
@@ -62,10 +62,10 @@ force_scatter_kernel(int n_centers, const int32_t* __restrict__ centers,
       for (int d = 0; d < D; d++)
       {
         const double wd = w[d];
-        const double* rp = blk + (int64_t) d * row + c0 + lane;
+        const TDz* rp = blk + (int64_t) d * row + c0 + lane;
 #pragma unroll
         for (int u = 0; u < SC_COLS; u++)
-          if (tgt[u] >= 0) acc[u] += wd * rp[u * 32];
+          if (tgt[u] >= 0) acc[u] += wd * (double) rp[u * 32];
       }
 #pragma unroll
       for (int u = 0; u < SC_COLS; u++)
@@ -75,11 +75,11 @@ force_scatter_kernel(int n_centers, const int32_t* __restrict__ centers,
     {
       for (int d = 0; d < D; d++)
       {
-        const double* rp = blk + (int64_t) d * row + c0 + lane;
+        const TDz* rp = blk + (int64_t) d * row + c0 + lane;
         double s = 0.0;
 #pragma unroll
         for (int u = 0; u < SC_COLS; u++)
-          if (tgt[u] >= 0) s += g[u] * rp[u * 32];
+          if (tgt[u] >= 0) s += g[u] * (double) rp[u * 32];
         s = warp_sum(s);
         if (lane == 0)
         {
@@ -95,11 +95,12 @@ force_scatter_kernel(int n_centers, const int32_t* __restrict__ centers,
 // Dense (N, D, 3N) and stress (N, D, 6) views, sym_fn.py:163-185.  One thread per (t, d);
 // slots are visited in list order, centre last — the reference's own accumulation order, so
 // the dense view is deterministic and needs no atomics.
+template <typename TDz>
 __global__ void __launch_bounds__(128)
 dense_fold_kernel(int n_centers, const int32_t* __restrict__ centers,
                   const int64_t* __restrict__ nl_off, const int32_t* __restrict__ nl_idx,
                   const int32_t* __restrict__ image, const double* __restrict__ coords, int D,
-                  int n_contrib, const double* __restrict__ dz, const int64_t* __restrict__ dz_ptr,
+                  int n_contrib, const TDz* __restrict__ dz, const int64_t* __restrict__ dz_ptr,
                   double* __restrict__ dense, double* __restrict__ stress)
 {
   const int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,13 +109,13 @@ dense_fold_kernel(int n_centers, const int32_t* __restrict__ centers,
   const int a = centers ? centers[t] : t;
   const int64_t off = nl_off[a];
   const int n = (int) (nl_off[a + 1] - off);
-  const double* rp = dz + dz_ptr[t] + (int64_t) d * 3 * (n + 1);
+  const TDz* rp = dz + dz_ptr[t] + (int64_t) d * 3 * (n + 1);
   double* drow = dense ? dense + ((int64_t) t * D + d) * 3 * n_contrib : nullptr;
   double s[6] = {0, 0, 0, 0, 0, 0};
   for (int slot = 0; slot <= n; slot++)
   {
     const int atom = slot < n ? nl_idx[off + slot] : a;
-    const double gx = rp[3 * slot], gy = rp[3 * slot + 1], gz = rp[3 * slot + 2];
+    const double gx = (double) rp[3 * slot], gy = (double) rp[3 * slot + 1], gz = (double) rp[3 * slot + 2];
     if (drow)
     {
       double* o = drow + 3 * image[atom];
@@ -136,16 +137,21 @@ dense_fold_kernel(int n_centers, const int32_t* __restrict__ centers,
 extern "C" int kb_force_scatter_fwd(int32_t n_centers, const int32_t* d_centers,
                                     const int64_t* d_nl_offsets, const int32_t* d_nl_indices,
                                     const int32_t* d_image, int32_t n_desc, const double* d_dEdG,
-                                    const double* d_scale, const double* d_dz,
+                                    const double* d_scale, const void* d_dz, int32_t dz_dtype,
                                     const int64_t* d_dz_ptr, double* d_forces, void* stream)
 {
-  if (n_centers < 0 || n_desc < 1) return KB_ERR_INVALID;
+  if (n_centers < 0 || n_desc < 1 || (dz_dtype != KB_F64 && dz_dtype != KB_F32)) return KB_ERR_INVALID;
   if (n_centers == 0) return KB_OK;
   const int nblk = (n_centers + SC_WARPS - 1) / SC_WARPS;
-  force_scatter_kernel<false><<<nblk, SC_WARPS * 32, sizeof(double) * SC_WARPS * n_desc,
-                                kb_stream(stream)>>>(n_centers, d_centers, d_nl_offsets,
-                                                     d_nl_indices, d_image, n_desc, d_dEdG, d_scale,
-                                                     d_dz, d_dz_ptr, d_forces);
+  const size_t smem = sizeof(double) * SC_WARPS * n_desc;
+  if (dz_dtype == KB_F64)
+    force_scatter_kernel<false, double><<<nblk, SC_WARPS * 32, smem, kb_stream(stream)>>>(
+        n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, n_desc, d_dEdG, d_scale,
+        static_cast<const double*>(d_dz), d_dz_ptr, d_forces);
+  else
+    force_scatter_kernel<false, float><<<nblk, SC_WARPS * 32, smem, kb_stream(stream)>>>(
+        n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, n_desc, d_dEdG, d_scale,
+        static_cast<const float*>(d_dz), d_dz_ptr, d_forces);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -153,16 +159,21 @@ extern "C" int kb_force_scatter_fwd(int32_t n_centers, const int32_t* d_centers,
 extern "C" int kb_force_scatter_bwd(int32_t n_centers, const int32_t* d_centers,
                                     const int64_t* d_nl_offsets, const int32_t* d_nl_indices,
                                     const int32_t* d_image, int32_t n_desc, const double* d_gF,
-                                    const double* d_scale, const double* d_dz,
+                                    const double* d_scale, const void* d_dz, int32_t dz_dtype,
                                     const int64_t* d_dz_ptr, double* d_gdEdG, void* stream)
 {
-  if (n_centers < 0 || n_desc < 1) return KB_ERR_INVALID;
+  if (n_centers < 0 || n_desc < 1 || (dz_dtype != KB_F64 && dz_dtype != KB_F32)) return KB_ERR_INVALID;
   if (n_centers == 0) return KB_OK;
   const int nblk = (n_centers + SC_WARPS - 1) / SC_WARPS;
-  force_scatter_kernel<true><<<nblk, SC_WARPS * 32, sizeof(double) * SC_WARPS * n_desc,
-                               kb_stream(stream)>>>(n_centers, d_centers, d_nl_offsets,
-                                                    d_nl_indices, d_image, n_desc, d_gF, d_scale,
-                                                    d_dz, d_dz_ptr, d_gdEdG);
+  const size_t smem = sizeof(double) * SC_WARPS * n_desc;
+  if (dz_dtype == KB_F64)
+    force_scatter_kernel<true, double><<<nblk, SC_WARPS * 32, smem, kb_stream(stream)>>>(
+        n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, n_desc, d_gF, d_scale,
+        static_cast<const double*>(d_dz), d_dz_ptr, d_gdEdG);
+  else
+    force_scatter_kernel<true, float><<<nblk, SC_WARPS * 32, smem, kb_stream(stream)>>>(
+        n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, n_desc, d_gF, d_scale,
+        static_cast<const float*>(d_dz), d_dz_ptr, d_gdEdG);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -170,15 +181,22 @@ extern "C" int kb_force_scatter_bwd(int32_t n_centers, const int32_t* d_centers,
 extern "C" int kb_dense_fold(int32_t n_centers, const int32_t* d_centers,
                              const int64_t* d_nl_offsets, const int32_t* d_nl_indices,
                              const int32_t* d_image, const double* d_coords, int32_t n_desc,
-                             int32_t n_contrib, const double* d_dz, const int64_t* d_dz_ptr,
-                             double* d_dense_forces, double* d_dense_stress, void* stream)
+                             int32_t n_contrib, const void* d_dz, int32_t dz_dtype,
+                             const int64_t* d_dz_ptr, double* d_dense_forces,
+                             double* d_dense_stress, void* stream)
 {
-  if (n_centers < 0 || n_desc < 1) return KB_ERR_INVALID;
+  if (n_centers < 0 || n_desc < 1 || (dz_dtype != KB_F64 && dz_dtype != KB_F32)) return KB_ERR_INVALID;
   if (n_centers == 0 || (!d_dense_forces && !d_dense_stress)) return KB_OK;
   const int64_t items = (int64_t) n_centers * n_desc;
-  dense_fold_kernel<<<(unsigned) ((items + 127) / 128), 128, 0, kb_stream(stream)>>>(
-      n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, d_coords, n_desc, n_contrib, d_dz,
-      d_dz_ptr, d_dense_forces, d_dense_stress);
+  const unsigned nblk = (unsigned) ((items + 127) / 128);
+  if (dz_dtype == KB_F64)
+    dense_fold_kernel<double><<<nblk, 128, 0, kb_stream(stream)>>>(
+        n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, d_coords, n_desc, n_contrib,
+        static_cast<const double*>(d_dz), d_dz_ptr, d_dense_forces, d_dense_stress);
+  else
+    dense_fold_kernel<float><<<nblk, 128, 0, kb_stream(stream)>>>(
+        n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, d_coords, n_desc, n_contrib,
+        static_cast<const float*>(d_dz), d_dz_ptr, d_dense_forces, d_dense_stress);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

@@ -4,19 +4,19 @@
 int kb_symfun_general_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
                              const int32_t* d_subset, const double* d_coords,
                              const int32_t* d_species, const int64_t* d_nl_off,
-                             const int32_t* d_nl_idx, double* d_zeta, double* d_dz,
+                             const int32_t* d_nl_idx, double* d_zeta, void* d_dz, int dz_dtype,
                              const int64_t* d_dz_ptr, cudaStream_t st);
 int kb_symfun_tiled_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
                            const double* d_coords, const int32_t* d_species,
                            const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn,
-                           double* d_zeta, double* d_dz, const int64_t* d_dz_ptr,
+                           double* d_zeta, void* d_dz, int dz_dtype, const int64_t* d_dz_ptr,
                            int32_t* d_overflow, bool* may_overflow, cudaStream_t st);
 
 int kb_symfun_warp_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
                           const int32_t* d_subset, const double* d_coords, const int32_t* d_species,
                           const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn, double* d_zeta,
-                          double* d_dz, const int64_t* d_dz_ptr, int32_t* d_overflow, int full_capacity,
-                          bool* launched, bool* may_overflow, cudaStream_t st);
+                          void* d_dz, int dz_dtype, const int64_t* d_dz_ptr, int32_t* d_overflow,
+                          int full_capacity, bool* launched, bool* may_overflow, cudaStream_t st);
 
 namespace {
 
@@ -84,11 +84,13 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
                                  const int32_t* d_centers, const double* d_coords,
                                  const int32_t* d_species, const int64_t* d_nl_offsets,
                                  const int32_t* d_nl_indices, int32_t maxn, double* d_zeta,
-                                 double* d_dz, const int64_t* d_dz_ptr, int32_t mode, void* stream)
+                                 void* d_dz, int32_t dz_dtype, const int64_t* d_dz_ptr,
+                                 int32_t mode, void* stream)
 {
   int rc = validate(h_params);
   if (rc) return rc;
   if (n_centers < 0 || !d_zeta || (d_dz && !d_dz_ptr) || maxn < 0) return KB_ERR_INVALID;
+  if (dz_dtype != KB_F64 && dz_dtype != KB_F32) return KB_ERR_INVALID;
   if (n_centers == 0) return KB_OK;
   cudaStream_t st = kb_stream(stream);
   kb_pool_setup();
@@ -96,7 +98,7 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
 
   if (mode == KB_SYMFUN_GENERAL)
     return kb_symfun_general_launch(P, n_centers, d_centers, nullptr, d_coords, d_species,
-                                    d_nl_offsets, d_nl_indices, d_zeta, d_dz, d_dz_ptr, st);
+                                    d_nl_offsets, d_nl_indices, d_zeta, d_dz, dz_dtype, d_dz_ptr, st);
 
   // ---- preferred: warp-per-atom kernel (g4 sets with canonical exponents, n <= 64)
   if (mode == KB_SYMFUN_AUTO || mode == KB_SYMFUN_WARP)
@@ -106,7 +108,7 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
     KB_CUDA(cudaMemsetAsync(ov, 0, 2 * sizeof(int32_t), st));
     bool launched = false, may_overflow = false;
     rc = kb_symfun_warp_launch(P, n_centers, d_centers, nullptr, d_coords, d_species, d_nl_offsets,
-                               d_nl_indices, maxn, d_zeta, d_dz, d_dz_ptr, ov, 0, &launched,
+                               d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov, 0, &launched,
                                &may_overflow, st);
     if (rc == KB_OK && launched && may_overflow)
     {
@@ -122,7 +124,7 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
         KB_CUDA(cudaMemsetAsync(ov2, 0, 2 * sizeof(int32_t), st));
         bool l2 = false, m2 = false;
         rc = kb_symfun_warp_launch(P, n_over, d_centers, ov + 2, d_coords, d_species, d_nl_offsets,
-                                   d_nl_indices, maxn, d_zeta, d_dz, d_dz_ptr, ov2, 1, &l2, &m2, st);
+                                   d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov2, 1, &l2, &m2, st);
         int32_t n_over2 = l2 ? 0 : n_over;
         if (rc == KB_OK && l2 && m2)
         {
@@ -132,7 +134,7 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
         }
         if (rc == KB_OK && n_over2 > 0)  // n > 64 (or nothing fits): global-atomics kernel
           rc = kb_symfun_general_launch(P, n_over2, d_centers, l2 ? ov2 + 2 : ov + 2, d_coords,
-                                        d_species, d_nl_offsets, d_nl_indices, d_zeta, d_dz, d_dz_ptr, st);
+                                        d_species, d_nl_offsets, d_nl_indices, d_zeta, d_dz, dz_dtype, d_dz_ptr, st);
         cudaFreeAsync(ov2, st);
       }
     }
@@ -147,7 +149,7 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
   KB_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), st));
   bool may_overflow = false;
   rc = kb_symfun_tiled_launch(P, n_centers, d_centers, d_coords, d_species, d_nl_offsets,
-                              d_nl_indices, maxn, d_zeta, d_dz, d_dz_ptr, d_overflow,
+                              d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, d_overflow,
                               &may_overflow, st);
   if (rc == KB_OK && may_overflow)
   {
@@ -161,7 +163,7 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
       if (mode == KB_SYMFUN_TILED) rc = KB_ERR_LIMIT;
       else
         rc = kb_symfun_general_launch(P, n_over, d_centers, d_overflow + 1, d_coords, d_species,
-                                      d_nl_offsets, d_nl_indices, d_zeta, d_dz, d_dz_ptr, st);
+                                      d_nl_offsets, d_nl_indices, d_zeta, d_dz, dz_dtype, d_dz_ptr, st);
     }
   }
   cudaFreeAsync(d_overflow, st);

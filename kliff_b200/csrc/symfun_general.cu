@@ -13,12 +13,13 @@ namespace {
 
 constexpr int GEN_WARPS = 4;
 
+template <typename TOut>
 __global__ void __launch_bounds__(GEN_WARPS * 32)
 symfun_general_kernel(const __grid_constant__ kb_symfun_params P, int n_centers,
                       const int32_t* __restrict__ centers, const int32_t* __restrict__ subset,
                       const double* __restrict__ coords, const int32_t* __restrict__ species,
                       const int64_t* __restrict__ nl_off, const int32_t* __restrict__ nl_idx,
-                      double* __restrict__ zeta, double* __restrict__ dz,
+                      double* __restrict__ zeta, TOut* __restrict__ dz,
                       const int64_t* __restrict__ dz_ptr)
 {
   extern __shared__ double zacc_all[];  // [GEN_WARPS][D]
@@ -33,14 +34,14 @@ symfun_general_kernel(const __grid_constant__ kb_symfun_params P, int n_centers,
   const int n = (int) (nl_off[i + 1] - off);
   const int32_t* nb = nl_idx + off;
   const bool grad = dz != nullptr;
-  double* blk = grad ? dz + dz_ptr[t] : nullptr;
+  TOut* blk = grad ? dz + dz_ptr[t] : nullptr;
   const int64_t row = 3LL * (n + 1);
 
   for (int d = lane; d < D; d += 32) zacc[d] = 0.0;
   if (grad)
   {
     const int64_t len = dz_ptr[t + 1] - dz_ptr[t];
-    for (int64_t e = lane; e < len; e += 32) blk[e] = 0.0;
+    for (int64_t e = lane; e < len; e += 32) blk[e] = (TOut) 0;
   }
   __syncwarp();
 
@@ -72,13 +73,13 @@ symfun_general_kernel(const __grid_constant__ kb_symfun_params P, int n_centers,
       if (lane == 0) zacc[P.two_out[q]] += tot;
       if (grad && on)
       {
-        double* rowp = blk + P.two_out[q] * row;
+        TOut* rowp = blk + P.two_out[q] * row;
 #pragma unroll
         for (int c = 0; c < 3; c++)
         {
           const double pr = dphi * v[c] / r;
-          atomicAdd(rowp + 3 * jj + c, pr);
-          atomicAdd(rowp + 3 * n + c, -pr);
+          atomicAdd(rowp + 3 * jj + c, (TOut) pr);
+          atomicAdd(rowp + 3 * n + c, (TOut) -pr);
         }
       }
     }
@@ -138,16 +139,16 @@ symfun_general_kernel(const __grid_constant__ kb_symfun_params P, int n_centers,
             if (lane == 0) zacc[d] += tot;
             if (grad && live)
             {
-              double* rowp = blk + d * row;
+              TOut* rowp = blk + d * row;
 #pragma unroll
               for (int c = 0; c < 3; c++)
               {
                 const double pij = dphi[0] * vij[c] / r[0];  // :583-593
                 const double pik = dphi[1] * vik[c] / r[1];
                 const double pjk = dphi[2] * vjk[c] / r[2];
-                atomicAdd(rowp + 3 * n + c, -pij - pik);
-                atomicAdd(rowp + 3 * jj + c, pij - pjk);
-                atomicAdd(rowp + 3 * kk + c, pik + pjk);
+                atomicAdd(rowp + 3 * n + c, (TOut) (-pij - pik));
+                atomicAdd(rowp + 3 * jj + c, (TOut) (pij - pjk));
+                atomicAdd(rowp + 3 * kk + c, (TOut) (pik + pjk));
               }
             }
           }
@@ -164,15 +165,20 @@ symfun_general_kernel(const __grid_constant__ kb_symfun_params P, int n_centers,
 int kb_symfun_general_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
                              const int32_t* d_subset, const double* d_coords,
                              const int32_t* d_species, const int64_t* d_nl_off,
-                             const int32_t* d_nl_idx, double* d_zeta, double* d_dz,
+                             const int32_t* d_nl_idx, double* d_zeta, void* d_dz, int dz_dtype,
                              const int64_t* d_dz_ptr, cudaStream_t st)
 {
   if (n_centers <= 0) return KB_OK;
   const int nblk = (n_centers + GEN_WARPS - 1) / GEN_WARPS;
   const size_t smem = sizeof(double) * GEN_WARPS * (size_t) P.n_desc;
-  symfun_general_kernel<<<nblk, GEN_WARPS * 32, smem, st>>>(P, n_centers, d_centers, d_subset,
-                                                            d_coords, d_species, d_nl_off,
-                                                            d_nl_idx, d_zeta, d_dz, d_dz_ptr);
+  if (dz_dtype == KB_F32)
+    symfun_general_kernel<float><<<nblk, GEN_WARPS * 32, smem, st>>>(
+        P, n_centers, d_centers, d_subset, d_coords, d_species, d_nl_off, d_nl_idx, d_zeta,
+        static_cast<float*>(d_dz), d_dz_ptr);
+  else
+    symfun_general_kernel<double><<<nblk, GEN_WARPS * 32, smem, st>>>(
+        P, n_centers, d_centers, d_subset, d_coords, d_species, d_nl_off, d_nl_idx, d_zeta,
+        static_cast<double*>(d_dz), d_dz_ptr);
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

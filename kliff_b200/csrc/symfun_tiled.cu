@@ -44,7 +44,7 @@ struct TiledArgs
   const int64_t* nl_off;
   const int32_t* nl_idx;
   double* zeta;
-  double* dz;
+  void* dz;
   const int64_t* dz_ptr;
   int32_t* overflow;  // [0] = count, [1..] = centre ordinals to redo with the general kernel
   int NP;             // neighbor capacity (even, <= 64)
@@ -68,7 +68,7 @@ __host__ __device__ inline size_t tiled_smem_bytes(const kb_symfun_params& P, in
   return (bytes + 15) & ~(size_t) 15;
 }
 
-template <int ZLK, bool GRAD>
+template <int ZLK, bool GRAD, typename TOut>
 __global__ void __launch_bounds__(TT, 2)
 symfun_tiled_kernel(const __grid_constant__ kb_symfun_params P, const TiledArgs A)
 {
@@ -417,17 +417,25 @@ symfun_tiled_kernel(const __grid_constant__ kb_symfun_params P, const TiledArgs 
     const int64_t o0 = A.dz_ptr[t];
     const int len = (int) (A.dz_ptr[t + 1] - o0);  // padded to a multiple of 16 doubles
     const int exact = D * row;
-    double2* out = reinterpret_cast<double2*>(A.dz + o0);
-    const double2* in = reinterpret_cast<const double2*>(stage);
-    for (int q = tid; q < len / 2; q += TT)
+    if (sizeof(TOut) == 8)
     {
-      double2 v = in[q];
-      if (2 * q + 1 >= exact)
+      double2* out = reinterpret_cast<double2*>(static_cast<double*>(A.dz) + o0);
+      const double2* in = reinterpret_cast<const double2*>(stage);
+      for (int q = tid; q < len / 2; q += TT)
       {
-        if (2 * q >= exact) v.x = 0.0;
-        v.y = 0.0;
+        double2 v = in[q];
+        if (2 * q + 1 >= exact)
+        {
+          if (2 * q >= exact) v.x = 0.0;
+          v.y = 0.0;
+        }
+        out[q] = v;
       }
-      out[q] = v;
+    }
+    else
+    {
+      TOut* out = static_cast<TOut*>(A.dz) + o0;
+      for (int q = tid; q < len; q += TT) out[q] = q < exact ? (TOut) stage[q] : (TOut) 0;
     }
   }
 }
@@ -437,7 +445,7 @@ symfun_tiled_kernel(const __grid_constant__ kb_symfun_params P, const TiledArgs 
 int kb_symfun_tiled_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
                            const double* d_coords, const int32_t* d_species,
                            const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn,
-                           double* d_zeta, double* d_dz, const int64_t* d_dz_ptr,
+                           double* d_zeta, void* d_dz, int dz_dtype, const int64_t* d_dz_ptr,
                            int32_t* d_overflow, bool* may_overflow, cudaStream_t st)
 {
   *may_overflow = false;
@@ -471,19 +479,24 @@ int kb_symfun_tiled_launch(const kb_symfun_params& P, int n_centers, const int32
   A.overflow = d_overflow; A.NP = NP; A.RC = RC; A.NGP = NGP; A.NPW = NPW;
   A.stage_elems = stage_elems; A.has_g5 = has_g5;
 
-#define KB_TILED_LAUNCH(Z, G)                                                                   \
+#define KB_TILED_LAUNCH(Z, G, T)                                                                \
   do {                                                                                          \
-    KB_CUDA(cudaFuncSetAttribute(symfun_tiled_kernel<Z, G>,                                     \
+    KB_CUDA(cudaFuncSetAttribute(symfun_tiled_kernel<Z, G, T>,                                  \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));     \
-    symfun_tiled_kernel<Z, G><<<n_centers, TT, smem, st>>>(P, A);                               \
+    symfun_tiled_kernel<Z, G, T><<<n_centers, TT, smem, st>>>(P, A);                            \
   } while (0)
+  const bool f32 = dz_dtype == KB_F32;
   if (P.canonical_zl)
   {
-    if (grad) KB_TILED_LAUNCH(1, true); else KB_TILED_LAUNCH(1, false);
+    if (!grad) KB_TILED_LAUNCH(1, false, double);
+    else if (f32) KB_TILED_LAUNCH(1, true, float);
+    else KB_TILED_LAUNCH(1, true, double);
   }
   else
   {
-    if (grad) KB_TILED_LAUNCH(0, true); else KB_TILED_LAUNCH(0, false);
+    if (!grad) KB_TILED_LAUNCH(0, false, double);
+    else if (f32) KB_TILED_LAUNCH(0, true, float);
+    else KB_TILED_LAUNCH(0, true, double);
   }
 #undef KB_TILED_LAUNCH
   KB_LAUNCH_CHECK();

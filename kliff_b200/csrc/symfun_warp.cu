@@ -69,7 +69,7 @@ struct WarpArgs
   const int64_t* nl_off;
   const int32_t* nl_idx;
   double* zeta;
-  double* dz;
+  void* dz;           // packed blocks, element type chosen by the kernel template
   const int64_t* dz_ptr;
   int32_t* overflow;  // [0] count, [1] work counter, [2..] ordinals this kernel declined
   int NP;             // neighbor capacity (even, <= 64)
@@ -89,7 +89,7 @@ __host__ __device__ inline size_t warp_smem_bytes(const kb_symfun_params& P, int
   return (bytes + 15) & ~(size_t) 15;
 }
 
-template <bool GRAD>
+template <bool GRAD, typename TOut>
 __global__ void __launch_bounds__(32, GRAD ? KB_WARP_MIN_BLOCKS : KB_WARP_MIN_BLOCKS_NOGRAD)
 symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
 {
@@ -152,7 +152,7 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
     const int si = A.species[i];
     const double xi = A.coords[3 * i], yi = A.coords[3 * i + 1], zi = A.coords[3 * i + 2];
     const int row = 3 * (n + 1);
-    double* blk = GRAD ? A.dz + A.dz_ptr[t] : nullptr;
+    TOut* blk = GRAD ? static_cast<TOut*>(A.dz) + A.dz_ptr[t] : nullptr;
     double* zrow = A.zeta + (int64_t) t * D;
 
     for (int q = lane; q < 4 * NT; q += 32) Z2[q] = 0.0;
@@ -198,8 +198,8 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
           const double px = dphi * ux, py = dphi * uy, pz = dphi * uz;  // :497
           if (GRAD && q < NT && jj < n)
           {
-            double* o = blk + (int64_t) P.two_out[q] * row + 3 * jj;
-            o[0] = px; o[1] = py; o[2] = pz;
+            TOut* o = blk + (int64_t) P.two_out[q] * row + 3 * jj;
+            o[0] = (TOut) px; o[1] = (TOut) py; o[2] = (TOut) pz;
           }
           v[4 * u] = phi; v[4 * u + 1] = px; v[4 * u + 2] = py; v[4 * u + 3] = pz;
         }
@@ -218,8 +218,8 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       zrow[P.two_out[q]] = Z2[q];
       if (GRAD)
       {
-        double* o = blk + (int64_t) P.two_out[q] * row + 3 * n;  // centre slot, :499-501
-        o[0] = -Z2[NT + 3 * q]; o[1] = -Z2[NT + 3 * q + 1]; o[2] = -Z2[NT + 3 * q + 2];
+        TOut* o = blk + (int64_t) P.two_out[q] * row + 3 * n;  // centre slot, :499-501
+        o[0] = (TOut) -Z2[NT + 3 * q]; o[1] = (TOut) -Z2[NT + 3 * q + 1]; o[2] = (TOut) -Z2[NT + 3 * q + 2];
       }
     }
 
@@ -445,8 +445,9 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
             csum[e][0] += acc[e][0]; csum[e][1] += acc[e][1]; csum[e][2] += acc[e][2];
             if (gout[e] >= 0)
             {
-              double* o = blk + (int64_t) gout[e] * row + 3 * k;
-              o[0] = p2tab[e] * acc[e][0]; o[1] = p2tab[e] * acc[e][1]; o[2] = p2tab[e] * acc[e][2];
+              TOut* o = blk + (int64_t) gout[e] * row + 3 * k;
+              o[0] = (TOut) (p2tab[e] * acc[e][0]); o[1] = (TOut) (p2tab[e] * acc[e][1]);
+              o[2] = (TOut) (p2tab[e] * acc[e][2]);
             }
           }
         }
@@ -472,15 +473,16 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
         zrow[gout[e]] = 0.5 * p2tab[e] * zsum[e];  // each unordered triple was visited twice
         if (GRAD)
         {
-          double* o = blk + (int64_t) gout[e] * row + 3 * n;
-          o[0] = -p2tab[e] * csum[e][0]; o[1] = -p2tab[e] * csum[e][1]; o[2] = -p2tab[e] * csum[e][2];
+          TOut* o = blk + (int64_t) gout[e] * row + 3 * n;
+          o[0] = (TOut) (-p2tab[e] * csum[e][0]); o[1] = (TOut) (-p2tab[e] * csum[e][1]);
+          o[2] = (TOut) (-p2tab[e] * csum[e][2]);
         }
       }
     }
     if (GRAD)
     {
       const int len = (int) (A.dz_ptr[t + 1] - A.dz_ptr[t]);
-      for (int q = D * row + lane; q < len; q += 32) blk[q] = 0.0;  // alignment padding
+      for (int q = D * row + lane; q < len; q += 32) blk[q] = (TOut) 0;  // alignment padding
     }
     __syncwarp();
   }
@@ -492,8 +494,8 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
 int kb_symfun_warp_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
                           const int32_t* d_subset, const double* d_coords, const int32_t* d_species,
                           const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn, double* d_zeta,
-                          double* d_dz, const int64_t* d_dz_ptr, int32_t* d_overflow, int full_capacity,
-                          bool* launched, bool* may_overflow, cudaStream_t st)
+                          void* d_dz, int dz_dtype, const int64_t* d_dz_ptr, int32_t* d_overflow,
+                          int full_capacity, bool* launched, bool* may_overflow, cudaStream_t st)
 {
   *launched = false;
   *may_overflow = false;
@@ -555,16 +557,16 @@ int kb_symfun_warp_launch(const kb_symfun_params& P, int n_centers, const int32_
   int grid = sms * per_sm;
   if (grid > n_centers) grid = n_centers;
   const bool grad = d_dz != nullptr;
-  if (grad)
-  {
-    KB_CUDA(cudaFuncSetAttribute(symfun_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    symfun_warp_kernel<true><<<grid, 32, smem, st>>>(P, A);
-  }
-  else
-  {
-    KB_CUDA(cudaFuncSetAttribute(symfun_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    symfun_warp_kernel<false><<<grid, 32, smem, st>>>(P, A);
-  }
+#define KB_WARP_LAUNCH(G, T)                                                                        \
+  do {                                                                                              \
+    KB_CUDA(cudaFuncSetAttribute(symfun_warp_kernel<G, T>,                                          \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));         \
+    symfun_warp_kernel<G, T><<<grid, 32, smem, st>>>(P, A);                                         \
+  } while (0)
+  if (!grad) KB_WARP_LAUNCH(false, double);
+  else if (dz_dtype == KB_F32) KB_WARP_LAUNCH(true, float);
+  else KB_WARP_LAUNCH(true, double);
+#undef KB_WARP_LAUNCH
   KB_LAUNCH_CHECK();
   *launched = true;
   return KB_OK;

@@ -110,7 +110,8 @@ class CalculatorTorch:
             return None
         dev = self.model.device
         packed = PackedFingerprints.from_packed_gradients(
-            self.model.descriptor.get_size(), dev, [s["dzetadr_forces"] for s in samples])
+            self.model.descriptor.get_size(), dev, [s["dzetadr_forces"] for s in samples],
+            dz_dtype=torch.float32 if self.dtype == np.float32 else torch.float64)
         zeta = np.concatenate([np.asarray(s["zeta"], np.float64) for s in samples])
         packed.zeta_normalized = torch.as_tensor(zeta, device=dev)
         packed.scale = None  # gradients on disk are already divided by stdev

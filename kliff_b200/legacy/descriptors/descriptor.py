@@ -42,7 +42,7 @@ class Descriptor:
     def transform(self, conf, fit_forces=False, fit_stress=False):
         raise NotImplementedError
 
-    def transform_packed(self, configs, grad=True):
+    def transform_packed(self, configs, grad=True, device=None, gradient_dtype=np.float64):
         raise NotImplementedError
 
     def write_kim_params(self, path, fname="descriptor.params"):
@@ -61,7 +61,8 @@ class Descriptor:
         else:
             dense_stress = fit_stress
         grad = fit_forces or fit_stress
-        packed = self.transform_packed(configs, grad=grad)
+        gdt = getattr(self, "gradient_dtype", None)
+        packed = self.transform_packed(configs, grad=grad, gradient_dtype=gdt if gdt is not None else self.dtype)
 
         has_mean_stdev = self.mean is not None and self.stdev is not None
         if self.normalize and not has_mean_stdev:

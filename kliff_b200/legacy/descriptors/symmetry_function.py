@@ -40,6 +40,10 @@ class SymmetryFunction(Descriptor):
         self.size = self.get_size()
         self._params = ops.build_params(self.hyperparams, self._rcut)
         self.kernel_mode = 0  # KB_SYMFUN_AUTO
+        # storage type of the packed dG/dr blocks kept by generate_fingerprints: None = follow
+        # `dtype` (the reference casts its fingerprints to `dtype`, float32 by default, after
+        # computing them in float64, descriptor.py:197-205); the arithmetic is fp64 either way
+        self.gradient_dtype = None
 
     # ------------------------------------------------------------------ setup (sym_fn.py:214-283)
     def _set_cutoff(self):
@@ -97,14 +101,17 @@ class SymmetryFunction(Descriptor):
         return dict(coords=d["coords"], code=code, image_local=d["image"], counts=d["counts"],
                     indices_local=d["indices"], n_contrib=n, maxn=d["maxn"]), nei
 
-    def transform_packed(self, configs, grad=True, device=None):
-        """Descriptors (+ packed dG/dr) of a list of configurations in one batched pass."""
+    def transform_packed(self, configs, grad=True, device=None, gradient_dtype=np.float64):
+        """Descriptors (+ packed dG/dr) of a list of configurations in one batched pass.
+        `gradient_dtype` is the storage type of the blocks (fp64 unless asked otherwise;
+        `generate_fingerprints` passes the descriptor's `dtype`, as the reference casts there)."""
         device = device if device is not None else default_device()
         if not isinstance(configs, (list, tuple)):
             configs = [configs]
         parts = [self._config_part(c, device)[0] for c in configs]
         packed = PackedFingerprints.from_parts(len(self), device, parts)
-        packed.compute(self._params, grad=grad, mode=self.kernel_mode)
+        packed.compute(self._params, grad=grad, mode=self.kernel_mode,
+                       dz_dtype=torch.float32 if gradient_dtype in (np.float32, torch.float32) else torch.float64)
         return packed
 
     def transform(self, conf, fit_forces=False, fit_stress=False):

@@ -24,6 +24,16 @@ def _ptr(t, byte_offset=0):
     return C.c_void_p(t.data_ptr() + byte_offset) if t is not None else C.c_void_p(0)
 
 
+def _dz_code(t):
+    """KB_F64 / KB_F32 for a packed-gradient tensor (or a torch / numpy dtype)."""
+    dt = t.dtype if torch.is_tensor(t) else t
+    if dt in (torch.float64, np.float64):
+        return _lib.KB_F64
+    if dt in (torch.float32, np.float32):
+        return _lib.KB_F32
+    raise TypeError(f"packed gradients are float64 or float32, not {dt}")
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -178,9 +188,10 @@ def block_offsets(n_centers, centers, offsets, n_desc):
 
 
 def symfun_forward(params, coords, species, offsets, indices, maxn, n_centers=None, centers=None,
-                   grad=True, mode=_lib.KB_SYMFUN_AUTO, dz_ptr=None, dz=None):
+                   grad=True, mode=_lib.KB_SYMFUN_AUTO, dz_ptr=None, dz=None, dz_dtype=torch.float64):
     """Descriptors (and packed dG/dr) of centre atoms.  Returns (zeta f64[n_centers, D],
-    dz f64[total] | None, dz_ptr i64[n_centers+1] | None)."""
+    dz [total] | None, dz_ptr i64[n_centers+1] | None).  Arithmetic is fp64; `dz_dtype` float32
+    rounds the finished blocks on the way out (half the memory and contraction traffic)."""
     _need_cuda(coords, species, offsets, indices, centers)
     if centers is not None:
         n_centers = centers.shape[0]
@@ -192,14 +203,15 @@ def symfun_forward(params, coords, species, offsets, indices, maxn, n_centers=No
     if grad:
         if dz_ptr is None:
             dz_ptr, total = block_offsets(n_centers, centers, offsets, D)
-            dz = torch.empty((total,), dtype=torch.float64, device=dev)
+            dz = torch.empty((total,), dtype=dz_dtype, device=dev)
     else:
         dz, dz_ptr = None, None
     if indices.numel() == 0:
         indices = torch.zeros((1,), dtype=torch.int32, device=dev)
     check(_lib.lib().kb_symfun_forward(C.byref(params), n_centers, _ptr(centers), _ptr(coords),
                                        _ptr(species), _ptr(offsets), _ptr(indices), int(maxn),
-                                       _ptr(zeta), _ptr(dz), _ptr(dz_ptr), int(mode), _stream()),
+                                       _ptr(zeta), _ptr(dz), _dz_code(dz) if dz is not None else 0,
+                                       _ptr(dz_ptr), int(mode), _stream()),
           "kb_symfun_forward")
     return zeta, dz, dz_ptr
 
@@ -239,7 +251,7 @@ def _scatter_fwd(dEdG, pack):
     idx = pack["indices"]
     check(_lib.lib().kb_force_scatter_fwd(n_centers, _ptr(pack.get("centers")), _ptr(pack["offsets"]),
                                           _ptr(idx), _ptr(pack["image"]), pack["D"], _ptr(dEdG),
-                                          _ptr(pack.get("scale")), _ptr(pack["dz"]),
+                                          _ptr(pack.get("scale")), _ptr(pack["dz"]), _dz_code(pack["dz"]),
                                           _ptr(pack["dz_ptr"]),
                                           _ptr(F, -24 * int(pack.get("out_base", 0))), _stream()),
           "kb_force_scatter_fwd")
@@ -254,7 +266,7 @@ def _scatter_bwd(gF, pack):
     check(_lib.lib().kb_force_scatter_bwd(n_centers, _ptr(pack.get("centers")), _ptr(pack["offsets"]),
                                           _ptr(pack["indices"]), _ptr(pack["image"]), pack["D"],
                                           _ptr(gF, -24 * int(pack.get("out_base", 0))),
-                                          _ptr(pack.get("scale")), _ptr(pack["dz"]),
+                                          _ptr(pack.get("scale")), _ptr(pack["dz"]), _dz_code(pack["dz"]),
                                           _ptr(pack["dz_ptr"]), _ptr(out), _stream()),
           "kb_force_scatter_bwd")
     return out
@@ -275,8 +287,9 @@ def dense_fold(pack, coords, n_contrib, want_forces=True, want_stress=False):
     stress = torch.empty((n_centers, D, 6), dtype=torch.float64, device=dev) if want_stress else None
     check(_lib.lib().kb_dense_fold(n_centers, _ptr(pack.get("centers")), _ptr(pack["offsets"]),
                                    _ptr(pack["indices"]), _ptr(pack["image"]), _ptr(coords), D,
-                                   int(n_contrib), _ptr(pack["dz"]), _ptr(pack["dz_ptr"]),
-                                   _ptr(dense), _ptr(stress), _stream()), "kb_dense_fold")
+                                   int(n_contrib), _ptr(pack["dz"]), _dz_code(pack["dz"]),
+                                   _ptr(pack["dz_ptr"]), _ptr(dense), _ptr(stress), _stream()),
+          "kb_dense_fold")
     return dense, stress
 
 

@@ -113,11 +113,11 @@ class PackedFingerprints:
         self.maxn = maxn
         return self
 
-    def compute(self, params, grad=True, mode=0):
+    def compute(self, params, grad=True, mode=0, dz_dtype=torch.float64):
         """Run the descriptor kernel over every centre atom (one launch)."""
         self.zeta, self.dz, self.dz_ptr = ops.symfun_forward(
             params, self.coords, self.code, self.offsets, self.indices, self.maxn,
-            centers=self.centers, grad=grad, mode=mode)
+            centers=self.centers, grad=grad, mode=mode, dz_dtype=dz_dtype)
         return self
 
     # ------------------------------------------------------------------ per-configuration views
@@ -153,7 +153,7 @@ class PackedFingerprints:
         n = hi - lo
         counts = self.counts_of(c).cpu().numpy()
         ptr = self.dz_ptr[lo:hi + 1].cpu().numpy()
-        raw = self.dz[int(ptr[0]):int(ptr[-1])]
+        raw = self.dz[int(ptr[0]):int(ptr[-1])].to(torch.float64)
         if inv_scale is not None:
             # blocks are [D][n+1][3]: scale row d by 1/stdev[d]
             raw = raw.clone()
@@ -169,7 +169,7 @@ class PackedFingerprints:
         return PackedGradient(vals.astype(dtype), counts.astype(np.int32), nbrs, image, self.D)
 
     @classmethod
-    def from_packed_gradients(cls, D, device, grads):
+    def from_packed_gradients(cls, D, device, grads, dz_dtype=torch.float64):
         """Rebuild the device store from PackedGradient objects (fingerprints loaded from disk).
         Coordinates are not needed for the force contraction and are left empty."""
         self = cls(D, device)
@@ -207,7 +207,7 @@ class PackedFingerprints:
         self.indices = torch.as_tensor(np.concatenate(indices).astype(np.int32), device=device)
         self.image = torch.as_tensor(np.concatenate(image).astype(np.int32), device=device)
         self.centers = torch.as_tensor(np.concatenate(centers).astype(np.int32), device=device)
-        self.dz = torch.as_tensor(flat, device=device)
+        self.dz = torch.as_tensor(flat, device=device).to(dz_dtype)
         self.dz_ptr = torch.as_tensor(ptr, device=device)
         self.atom_ptr = np.asarray(atom_ptr, np.int64)
         self.cfg_ptr = np.asarray(cfg_ptr, np.int64)

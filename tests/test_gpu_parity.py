@@ -318,3 +318,38 @@ def test_force_scatter_forward_backward(dev):
     v = torch.tensor(rng.normal(size=(n, D)), device=dev)
     (back,) = torch.autograd.grad(gw2, gF2, v)
     assert torch.allclose(back, ops.force_scatter(v, pack), rtol=1e-12, atol=1e-12)
+
+
+def test_float32_block_storage(dev, port):
+    """KB_F32: arithmetic stays fp64, the finished blocks are rounded to float on the way out
+    (the reference's default dtype=np.float32 cast, descriptor.py:197-205).  Every kernel that reads
+    or writes blocks is checked against its fp64 twin at float precision."""
+    g = load_golden("ref_run_si64_set51.npz")
+    fams = fams_from_npz(g)
+    r = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], 5.0)
+    n = r["n"]
+    code = torch.zeros(r["allc"].shape[0], dtype=torch.int32, device=dev)
+    P = ops.build_params(hp_from_fams(fams), g["rcut"])
+    ref_z, ref_dz, ptr = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"], n_centers=n)
+    for mode in (_lib.KB_SYMFUN_WARP, _lib.KB_SYMFUN_TILED, _lib.KB_SYMFUN_GENERAL):
+        z, dz, ptr32 = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
+                                          n_centers=n, mode=mode, dz_dtype=torch.float32)
+        assert dz.dtype == torch.float32 and torch.equal(ptr32, ptr)
+        assert torch.allclose(z, ref_z, rtol=1e-12, atol=0)  # zeta is fp64 either way
+        scale = float(ref_dz.abs().max())
+        if mode == _lib.KB_SYMFUN_GENERAL:  # accumulates in float atomics
+            assert float((dz.double() - ref_dz).abs().max()) <= 2e-6 * scale
+        else:                                # one rounding per element
+            assert torch.equal(dz, ref_dz.float())
+    pack64 = dict(offsets=r["offsets"], indices=r["indices"], image=r["image"], dz=ref_dz, dz_ptr=ptr, D=51, n_out=n)
+    pack32 = dict(pack64, dz=ref_dz.float())
+    w = torch.tensor(g["w"], device=dev)
+    F64, F32 = ops._scatter_fwd(w, pack64), ops._scatter_fwd(w, pack32)
+    assert float((F64 - F32).abs().max()) <= 1e-6 * float(F64.abs().max())
+    gF = torch.randn(3 * n, dtype=torch.float64, device=dev)
+    b64, b32 = ops._scatter_bwd(gF, pack64), ops._scatter_bwd(gF, pack32)
+    assert float((b64 - b32).abs().max()) <= 1e-6 * float(b64.abs().max())
+    d64, s64 = ops.dense_fold(pack64, r["allc"], n, True, True)
+    d32, s32 = ops.dense_fold(pack32, r["allc"], n, True, True)
+    assert float((d64 - d32).abs().max()) <= 1e-6 * float(d64.abs().max())
+    assert float((s64 - s32).abs().max()) <= 1e-6 * float(s64.abs().max())
