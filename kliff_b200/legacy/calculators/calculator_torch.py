@@ -179,9 +179,16 @@ class CalculatorTorch:
         zeta = (zparts[0] if len(zparts) == 1 else torch.cat(zparts)).to(dt)
         if want_forces:
             zeta = zeta.detach().requires_grad_(True)
-        natoms = np.array([int(P.cfg_ptr[i + 1] - P.cfg_ptr[i]) for i in cfg_indices], np.int64)
-        cfg_of_atom = torch.repeat_interleave(
-            torch.arange(len(natoms), device=dev), torch.as_tensor(natoms, device=dev))
+        cfg_indices = list(cfg_indices)
+        natoms = (P.cfg_ptr[1:] - P.cfg_ptr[:-1])[np.asarray(cfg_indices, dtype=np.int64)]
+        if getattr(P, "_natoms_dev", None) is None:
+            P._natoms_dev = torch.as_tensor(np.diff(P.cfg_ptr), device=dev)
+        if len(runs) == 1:
+            reps = P._natoms_dev[runs[0][0]:runs[0][1]]
+        else:
+            reps = P._natoms_dev.index_select(0, torch.as_tensor(cfg_indices, device=dev))
+        cfg_of_atom = torch.repeat_interleave(torch.arange(len(natoms), device=dev), reps,
+                                              output_size=zeta.shape[0])
         e_atom = self._model_energy(zeta, cfg_indices).reshape(-1)
         energy = torch.zeros(len(natoms), dtype=dt, device=dev).index_add(0, cfg_of_atom, e_atom)
         forces = None

@@ -232,28 +232,53 @@ class LossNeuralNetworkModel:
             loss = loss / nglobal
         return loss
 
+    def _weights_on_device(self):
+        """Per-configuration loss weights and atom counts as device tensors, built once per data set
+        (the reference reads them per configuration per step, loss.py:904-912)."""
+        calc = self.calculator
+        fp = calc.fingerprints_dataset.fp
+        key = (id(fp), len(fp))
+        if getattr(self, "_wcache_key", None) != key:
+            dev, dt = calc.model.device, calc.model.dtype
+            w = [s["configuration"].weight for s in fp]
+            P = calc._packed
+            nat = np.diff(P.cfg_ptr).astype(np.float64)
+            wc = np.array([x.config_weight for x in w], np.float64)
+            we = np.array([x.energy_weight for x in w], np.float64)
+            wf = np.array([x.forces_weight if x.forces_weight is not None else 0.0 for x in w], np.float64)
+            denom = nat if self.residual_data["normalize_by_natoms"] else np.ones_like(nat)
+            self._wcache = dict(
+                e=torch.as_tensor(wc * we / denom, device=dev).to(dt),
+                f=torch.as_tensor(wc * wf / denom, device=dev).to(dt),
+                n3=torch.as_tensor(3 * np.diff(P.cfg_ptr), device=dev))
+            self._wcache_key = key
+        return self._wcache
+
     def _loss_vectorized(self, batch):
         """Same arithmetic as `energy_forces_residual` + sum of squares, over the whole batch."""
         calc = self.calculator
         idx = [s["index"] for s in batch]
         energy, forces, natoms = calc.compute_packed(idx)
-        dev, dt = energy.device, energy.dtype
-        P, ref = calc._packed, calc._ref
-        wc = torch.as_tensor([s["configuration"].weight.config_weight for s in batch], device=dev, dtype=dt)
-        we = torch.as_tensor([s["configuration"].weight.energy_weight for s in batch], device=dev, dtype=dt)
-        nat = torch.as_tensor(natoms, device=dev, dtype=dt)
-        denom = nat if self.residual_data["normalize_by_natoms"] else torch.ones_like(nat)
-        idx_t = torch.as_tensor(idx, device=dev)
-        res_e = wc * we * (energy - ref["energy"].index_select(0, idx_t)) / denom
+        dev = energy.device
+        P, ref, W = calc._packed, calc._ref, self._weights_on_device()
+        run = _is_run(idx)
+        if run:
+            sl = slice(idx[0], idx[-1] + 1)
+            res_e = W["e"][sl] * (energy - ref["energy"][sl])
+        else:
+            idx_t = torch.as_tensor(idx, device=dev)
+            res_e = W["e"].index_select(0, idx_t) * (energy - ref["energy"].index_select(0, idx_t))
         loss = (res_e * res_e).sum()
         if calc.use_forces:
-            wf = torch.as_tensor([s["configuration"].weight.forces_weight for s in batch], device=dev, dtype=dt)
-            if _is_run(idx):
+            if run:
                 fref = ref["forces"][3 * int(P.cfg_ptr[idx[0]]):3 * int(P.cfg_ptr[idx[-1] + 1])]
+                per_comp = torch.repeat_interleave(W["f"][sl], W["n3"][sl], output_size=forces.shape[0])
             else:
                 fref = torch.cat([ref["forces"][3 * int(P.cfg_ptr[i]):3 * int(P.cfg_ptr[i + 1])]
                                   for i in idx])
-            per_comp = torch.repeat_interleave(wc * wf / denom, 3 * torch.as_tensor(natoms, device=dev))
+                per_comp = torch.repeat_interleave(W["f"].index_select(0, idx_t),
+                                                   W["n3"].index_select(0, idx_t),
+                                                   output_size=forces.shape[0])
             res_f = per_comp * (forces - fref)
             loss = loss + (res_f * res_f).sum()
         return loss

@@ -179,7 +179,7 @@ def test_calculator_torch_parameters_and_forces(workdir):
     calc.update_model_params(np.zeros(nparams))
     assert np.allclose(calc.get_opt_params(), 0.0)
     out = calc.compute(batch)
-    assert all(float(e) == 0.0 for e in out["energy"])
+    assert all(float(e.detach()) == 0.0 for e in out["energy"])
     assert all(torch.count_nonzero(f) == 0 for f in out["forces"])
     forces0 = out["forces"]
     calc.update_model_params(np.ones(nparams))
