@@ -250,7 +250,7 @@ def train_epoch_probe(ncfg, dev):
         t_three = time.time() - t0  # 2 optimisation epochs + the final loss pass
     return {"configs": ncfg, "atoms": 64 * ncfg, "create_s": t_create,
             "epoch_s": t_three / 3.0, "steps_per_epoch": (ncfg + 99) // 100,
-            "note": "epoch_s = (2 Adam epochs + final loss pass) / 3, batch 100, fp32 MLP, fp64 dG/dr"}
+            "note": "epoch_s = (2 Adam epochs + final loss pass) / 3, batch 100, fp32 MLP, dG/dr computed in fp64 and stored in fp32 (descriptor dtype, as the reference)"}
 
 
 # ------------------------------------------------------------------------------------------------
