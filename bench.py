@@ -194,6 +194,86 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def run_slab_workload(args, rank, world, dev):
+    """One periodic supercell of (world * nx) x nx x nx cells, slab r owned by rank r.  Step =
+    halo exchange (NCCL p2p) -> paddings along a2/a3 -> neighbor list -> descriptor + dG/dr of the
+    owned atoms -> force contraction with a fixed dE/dG -> reverse halo exchange of ghost forces."""
+    import torch
+    import torch.distributed as dist
+
+    from kliff_b200 import ops
+    from kliff_b200.legacy.descriptors import SymmetryFunction
+    from kliff_b200.parallel import SlabDecomposition
+
+    nx = args.nx
+    cell = np.diag([A_SI * nx * world, A_SI * nx, A_SI * nx])
+    _, pos = diamond(nx, seed=rank)
+    pos[:, 0] += A_SI * nx * rank              # this rank's slab of the global lattice
+    n = len(pos)
+    desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": RC}, hyperparams="set51", normalize=False,
+                            dtype=np.float64)
+    dd = SlabDecomposition(cell, [1, 1, 1], RC, rank=rank, world=world)
+    x_own = dd.wrap(torch.tensor(pos, device=dev))
+    owner = dd.owner(x_own)
+    keep = owner == rank                       # jitter can push a face atom across the slab boundary:
+    moved = int((~keep).sum())                 # such atoms are simply not simulated (counted below)
+    x_own = x_own[keep].contiguous()
+    n_own = x_own.shape[0]
+    code = torch.zeros(n_own, dtype=torch.int32, device=dev)
+    w = torch.randn(n_own, 51, dtype=torch.float64, device=dev, generator=torch.Generator(dev).manual_seed(rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        gx, gc = dd.exchange_halo(x_own, code)
+        fp = dd.local_fingerprints(desc, x_own, code, gx, gc)
+        F = dd.forces(w, fp)
+        return fp, F, gx.shape[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        fp, F, ng = step()
+        del fp
+        flush.fill_(1)
+    barrier()
+    launches0 = ops.launch_count()
+    ms = []
+    for _ in range(args.steps):
+        flush.fill_(0)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fp, F, ng = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+        npad, nloc = fp["n_pad"], fp["n_local"]
+        del fp
+    barrier()
+    launches = ops.launch_count() - launches0
+    tot = torch.tensor([sum(ms), float(n_own), float(F.sum(dim=0).abs().max())], dtype=torch.float64, device=dev)
+    tmax = tot.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    total_ms, atoms = float(tmax[0]), float(tot[1])
+    if rank == 0:
+        print(json.dumps({
+            "metric": "descriptor+dG/dr+forces atoms/sec (one supercell, spatial domains + ghost halos)",
+            "value": atoms * args.steps / (total_ms * 1e-3), "unit": "atoms/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"ONE diamond-Si supercell of {world * nx}x{nx}x{nx} cells ({int(atoms)} atoms), "
+                                   f"slab per GPU, halo {RC} A (BASELINE.json configs[3] style)",
+                       "atoms_per_gpu": n_own, "ghosts_rank0": int(ng), "paddings_rank0": int(npad),
+                       "local_atoms_rank0": int(nloc), "atoms_dropped_at_faces_rank0": moved,
+                       "l2": "256 MiB write between timed steps"},
+            "gpu_launches": int(launches)}))
+
+
 def train_epoch_probe(ncfg, dev):
     """Second half of BASELINE.json's metric ("train epoch time"): synthetic set of `ncfg` 64-atom
     diamond-Si configurations (2x2x2 cells, a ~ U(5.2, 5.7), jitter 0.1 A, seed = index; reference
@@ -262,6 +342,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=50, help="conventional cells per edge (50 -> 1M atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="supercell", choices=["supercell", "slab"],
+                    help="supercell: configs[1], one independent 1M-atom cell per GPU (default, the contract "
+                         "line); slab: configs[3]-style, ONE supercell of gpus x nx^3 cells split by spatial "
+                         "domain with ghost halos (NCCL halo + reverse force exchange inside the step)")
     ap.add_argument("--epoch-configs", type=int, default=1000,
                     help="size of the synthetic 64-atom-configuration set for the train_epoch probe (0 = off)")
     args = ap.parse_args()
@@ -288,6 +372,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops.device_info()  # raises unless sm_100
+    if args.workload == "slab":
+        run_slab_workload(args, rank, world, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- synthetic input, resident in HBM before the timed region
     cell, pos = diamond(args.nx, seed=rank)
