@@ -208,7 +208,8 @@ def run_slab_workload(args, rank, world, dev):
     nx = args.nx
     cell = np.diag([A_SI * nx * world, A_SI * nx, A_SI * nx])
     _, pos = diamond(nx, seed=rank)
-    pos[:, 0] += A_SI * nx * rank              # this rank's slab of the global lattice
+    pos[:, 0] += A_SI * nx * rank + A_SI / 8.0  # this rank's slab of the global lattice; the 1/8-cell
+    #                                             shift keeps jittered atoms off the slab boundaries
     n = len(pos)
     desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": RC}, hyperparams="set51", normalize=False,
                             dtype=np.float64)
