@@ -89,9 +89,9 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
 {
   int rc = validate(h_params);
   if (rc) return rc;
+  if (n_centers == 0) return KB_OK;
   if (n_centers < 0 || !d_zeta || (d_dz && !d_dz_ptr) || maxn < 0) return KB_ERR_INVALID;
   if (dz_dtype != KB_F64 && dz_dtype != KB_F32) return KB_ERR_INVALID;
-  if (n_centers == 0) return KB_OK;
   cudaStream_t st = kb_stream(stream);
   kb_pool_setup();
   const kb_symfun_params& P = *h_params;

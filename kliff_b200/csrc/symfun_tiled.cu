@@ -165,7 +165,8 @@ symfun_tiled_kernel(const __grid_constant__ kb_symfun_params P, const TiledArgs 
       (unsigned long long) (unsigned) CNT[1] | ((unsigned long long) (unsigned) CNT[2] << 32);
 
   // ---- phase B: which neighbor pairs (j<k) can contribute; record slots -------------------
-  for (int p0 = 0; p0 < n * n; p0 += TT)
+  // (nothing to do for radial-only parameter sets: no records, no triple loop)
+  for (int p0 = 0; p0 < (NG > 0 ? n * n : 0); p0 += TT)
   {
     const int p = p0 + tid;
     bool rec = false, hit4 = false;

@@ -353,3 +353,55 @@ def test_float32_block_storage(dev, port):
     d32, s32 = ops.dense_fold(pack32, r["allc"], n, True, True)
     assert float((d64 - d32).abs().max()) <= 1e-6 * float(d64.abs().max())
     assert float((s64 - s32).abs().max()) <= 1e-6 * float(s64.abs().max())
+
+
+def test_edge_cases_radial_only_isolated_atom_nonperiodic(dev, port):
+    """Radial-only hyper-parameters (no angular group), an isolated atom (empty neighbor list, its
+    block is just the centre slot), a non-periodic cluster and an empty centre list."""
+    from collections import OrderedDict
+    hp = OrderedDict()
+    hp["g2"] = [{"eta": 0.3, "Rs": 0.0}, {"eta": 1.0, "Rs": 1.0}]
+    hp["g1"] = None
+    rng = np.random.default_rng(12)
+    pos = np.concatenate([rng.random((20, 3)) * 6.0 + 2.0, [[40.0, 40.0, 40.0]]])  # last atom isolated
+    cell = np.eye(3) * 60.0
+    z = np.full(len(pos), 14, np.int32)
+    rc = np.array([[4.0]])
+    for hyper in (hp, get_set30()):
+        r = gpu_neighbors(dev, cell, [0, 0, 0], pos, z, 4.0)
+        assert r["pc"].shape[0] == 0 and int(r["counts"][-1]) == 0
+        P = ops.build_params(hyper, rc)
+        code = torch.zeros(len(pos), dtype=torch.int32, device=dev)
+        fams = orc.fams_from_hyperparams(hyper)
+        off, idx = r["offsets"].cpu().numpy(), r["indices"].cpu().numpy()
+        for mode in (_lib.KB_SYMFUN_AUTO, _lib.KB_SYMFUN_TILED, _lib.KB_SYMFUN_GENERAL):
+            zeta, dz, ptr = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
+                                               n_centers=len(pos), mode=mode)
+            ptr_h, dz_h = ptr.cpu().numpy(), dz.cpu().numpy()
+            for a in range(len(pos)):
+                nb = idx[off[a]:off[a + 1]]
+                oz, og = port.symfun_atom(rc, fams, a, pos, np.zeros(len(pos), np.int32), nb)
+                assert np.allclose(zeta[a].cpu().numpy(), oz, rtol=TOL, atol=TOL * max(1.0, np.abs(oz).max()))
+                blk = dz_h[ptr_h[a]:ptr_h[a] + 3 * P.n_desc * (len(nb) + 1)].reshape(P.n_desc, -1, 3)
+                assert rowwise_rel_err(blk, og) <= TOL
+            assert np.all(zeta[-1].cpu().numpy() == 0.0)  # the isolated atom
+        # no centres at all
+        zeta, dz, ptr = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"],
+                                           centers=torch.zeros(0, dtype=torch.int32, device=dev))
+        assert zeta.shape == (0, P.n_desc) and dz.numel() == 0
+
+
+def test_unknown_species_and_bad_hyperparams(dev):
+    from kliff_b200.dataset import Configuration
+    from kliff_b200.legacy.descriptors import SymmetryFunction, SymmetryFunctionError
+    with pytest.raises(SymmetryFunctionError):
+        SymmetryFunction({"Si-Si": 5.0}, "poly", "set51")
+    with pytest.raises(SymmetryFunctionError):
+        SymmetryFunction({"Si-Si": 5.0}, "cos", "set99")
+    with pytest.raises(SymmetryFunctionError):
+        SymmetryFunction({"Si-Si": 5.0}, "cos", {"g7": [{"eta": 1.0}]})
+    desc = SymmetryFunction({"Si-Si": 5.0}, "cos", "set30")
+    conf = Configuration(cell=np.eye(3) * 10, species=["Si", "Ge"], coords=np.array([[0.0, 0, 0], [2.0, 0, 0]]),
+                         PBC=[True] * 3)
+    with pytest.raises(SymmetryFunctionError):
+        desc.transform(conf)
