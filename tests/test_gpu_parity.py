@@ -405,3 +405,78 @@ def test_unknown_species_and_bad_hyperparams(dev):
                          PBC=[True] * 3)
     with pytest.raises(SymmetryFunctionError):
         desc.transform(conf)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_differential(dev, port, seed):
+    """Randomised differential test of the whole path against the oracle: random triclinic cells,
+    1-3 species with different pair cutoffs, random PBC, random subsets of the five families with
+    random (also non-canonical) hyper-parameters.  Neighbor system bit-exact, zeta / dG/dr 1e-10."""
+    from collections import OrderedDict
+    rng = np.random.default_rng(100 + seed)
+    cell = np.diag(rng.uniform(5.0, 9.0, 3)) + rng.normal(0, 0.6, (3, 3))
+    n = int(rng.integers(6, 48))
+    frac = rng.random((n, 3))
+    pos = frac @ cell
+    # push apart atoms that are too close (the reference rejects r < 1e-5, and r ~ 0.3 A is unphysical)
+    for _ in range(50):
+        d = np.linalg.norm(pos[:, None] - pos[None], axis=-1) + np.eye(n) * 10
+        i, j = np.unravel_index(np.argmin(d), d.shape)
+        if d[i, j] > 0.9:
+            break
+        pos[j] += rng.normal(0, 0.8, 3)
+    nsp = int(rng.integers(1, 4))
+    code = rng.integers(0, nsp, n).astype(np.int32)
+    zmap = np.array([14, 6, 8], np.int32)
+    rcut = rng.uniform(2.6, 4.4, (nsp, nsp))
+    rcut = (rcut + rcut.T) / 2
+    pbc = rng.integers(0, 2, 3)
+    hp = OrderedDict()
+    fam_order = list(rng.permutation(["g1", "g2", "g3", "g4", "g5"]))[: int(rng.integers(1, 6))]
+    canonical = bool(rng.integers(0, 2))
+    for f in fam_order:
+        k = int(rng.integers(1, 5))
+        if f == "g1":
+            hp[f] = None
+        elif f == "g2":
+            hp[f] = [{"eta": float(rng.uniform(0.01, 1.5)), "Rs": float(rng.uniform(0, 2))} for _ in range(k)]
+        elif f == "g3":
+            hp[f] = [{"kappa": float(rng.uniform(0.1, 2.0))} for _ in range(k)]
+        else:
+            rows = []
+            for _ in range(k):
+                if canonical and f == "g4":
+                    rows.append({"zeta": float(rng.choice([1, 2, 4, 16])), "lambda": float(rng.choice([-1, 1])),
+                                 "eta": float(rng.choice([0.01, 0.05, 0.2]))})
+                else:
+                    rows.append({"zeta": float(rng.uniform(0.5, 6.0)), "lambda": float(rng.uniform(-1, 1)),
+                                 "eta": float(rng.uniform(0.0, 0.3))})
+            hp[f] = rows
+    infl = float(rcut.max())
+    r = gpu_neighbors(dev, cell, pbc, pos, zmap[code], infl)
+    opc, ops_, opi = port.create_paddings(infl, cell, pbc, pos, zmap[code])
+    assert np.array_equal(opc, r["pc"].cpu().numpy()) and np.array_equal(opi, r["pi"].cpu().numpy())
+    allc = np.concatenate([pos, opc]) if len(opc) else pos
+    need = np.zeros(len(allc), np.int32)
+    need[:n] = 1
+    oc, oo, oi = port.build_neighbors(allc, infl, need)
+    oi = orc.canonical(oo, oi)
+    assert np.array_equal(oi, r["indices"].cpu().numpy()) and np.array_equal(oc, r["counts"].cpu().numpy())
+    image = np.concatenate([np.arange(n), opi]).astype(np.int64)
+    allcode = code[image].astype(np.int32)
+    P = ops.build_params(hp, rcut)
+    zeta, dz, ptr = ops.symfun_forward(P, r["allc"], torch.tensor(allcode, device=dev), r["offsets"],
+                                       r["indices"], r["maxn"], n_centers=n)
+    fams = orc.fams_from_hyperparams(hp)
+    oz, og = port.symfun_range(rcut, fams, 0, n, allc, allcode, oo, oi)
+    D = P.n_desc
+    scale = np.maximum(np.abs(oz).max(axis=0), 1e-300)
+    assert np.max(np.abs(zeta.cpu().numpy() - oz) / scale) <= TOL
+    ptr_h, dz_h = ptr.cpu().numpy(), dz.cpu().numpy()
+    for t in range(n):
+        ref = og[3 * D * int(oo[t] + t):3 * D * int(oo[t + 1] + t + 1)].reshape(D, -1, 3)
+        blk = dz_h[ptr_h[t]:ptr_h[t] + ref.size].reshape(ref.shape)
+        # rows whose gradient vanishes identically are compared absolutely
+        rs = np.abs(ref).reshape(D, -1).max(axis=1)
+        err = np.abs(blk - ref).reshape(D, -1).max(axis=1)
+        assert np.all(err <= TOL * np.maximum(rs, 1e-12)), (seed, t, float((err / np.maximum(rs, 1e-12)).max()))
