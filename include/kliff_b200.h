@@ -129,6 +129,34 @@ int kb_nl_finish(kb_nl_plan* plan, int32_t* d_indices, void* stream);
 void kb_nl_destroy(kb_nl_plan* plan, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Batched paddings + neighbor lists for MANY configurations in one call — replaces the        */
+/* per-configuration loop `for conf in configs: NeighborList(conf, infl_dist, padding_need_    */
+/* neigh=False)` of Descriptor.generate_fingerprints / SymmetryFunction.transform              */
+/* (descriptor.py:186-238, sym_fn.py:118-133 -> neighbor.py:88-126).                           */
+/* One CTA per configuration; per configuration the result equals kb_pad_* followed by         */
+/* kb_nl_* bit for bit.  Output is the packed batch layout: per configuration its              */
+/* contributing atoms then its image atoms, atom ids global to the batch.                      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct kb_batch_plan kb_batch_plan;
+/* h_cfg_ptr[n_cfg+1]: contributing-atom range of every configuration in d_coords[.,3];
+ * h_cells[n_cfg*9] (rows = lattice vectors); h_pbc[n_cfg*3].  Counts image atoms
+ * (synchronises once) and returns the total number of atoms (contributing + images). */
+int kb_batch_begin(int32_t n_cfg, const int32_t* h_cfg_ptr, const double* h_cells,
+                   const int32_t* h_pbc, double cutoff, const double* d_coords,
+                   int64_t* h_total_atoms, kb_batch_plan** plan, void* stream);
+/* Writes d_coords_all[A,3], d_image[A] (global ordinal of the owning contributing atom),
+ * d_centers[n_contrib] (atom id of every contributing atom), d_atom_ptr[n_cfg+1], d_counts[A],
+ * d_offsets[A+1]; returns the number of neighbor indices and the longest list (synchronises
+ * once).  KB_ERR_REFERENCE on atom collisions (neighbor_list.cpp:199). */
+int kb_batch_neighbors(kb_batch_plan* plan, double* d_coords_all, int32_t* d_image,
+                       int32_t* d_centers, int64_t* d_atom_ptr, int32_t* d_counts,
+                       int64_t* d_offsets, int64_t* h_total_pairs, int32_t* h_maxn, void* stream);
+/* Writes the neighbor indices (ascending per atom, asynchronous) and frees the plan. */
+int kb_batch_finish(kb_batch_plan* plan, const double* d_coords_all, const int64_t* d_offsets,
+                    int32_t* d_indices, void* stream);
+void kb_batch_destroy(kb_batch_plan* plan, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Symmetry functions + dG/dr — replaces the per-atom loop over sf.Descriptor.generate_one_atom */
 /* (sym_fn.py:155-160 -> sym_fn_bind.cpp:38-94 -> sym_fn.cpp:416-602).                         */
 /*                                                                                            */

@@ -46,6 +46,7 @@ EXPORTS = [
     "kb_version", "kb_error_string", "kb_device_info",
     "kb_pad_begin", "kb_pad_finish", "kb_pad_destroy",
     "kb_nl_begin", "kb_nl_finish", "kb_nl_destroy",
+    "kb_batch_begin", "kb_batch_neighbors", "kb_batch_finish", "kb_batch_destroy",
     "kb_symfun_block_offsets", "kb_symfun_forward",
     "kb_force_scatter_fwd", "kb_force_scatter_bwd", "kb_dense_fold",
     "kb_probe_fp64_peak", "kb_probe_hbm_copy", "kb_launch_count",
@@ -88,6 +89,11 @@ def lib():
     L.kb_nl_finish.argtypes = [vp, vp, vp]
     L.kb_nl_destroy.argtypes = [vp, vp]
     L.kb_nl_destroy.restype = None
+    L.kb_batch_begin.argtypes = [i32, vp, vp, vp, dbl, vp, C.POINTER(i64), C.POINTER(vp), vp]
+    L.kb_batch_neighbors.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i32), vp]
+    L.kb_batch_finish.argtypes = [vp, vp, vp, vp, vp]
+    L.kb_batch_destroy.argtypes = [vp, vp]
+    L.kb_batch_destroy.restype = None
     L.kb_symfun_block_offsets.argtypes = [i32, vp, vp, i32, vp, C.POINTER(i64), vp]
     L.kb_symfun_forward.argtypes = [C.POINTER(kb_symfun_params), i32, vp, vp, vp, vp, vp, i32, vp,
                                     vp, i32, vp, i32, vp]

@@ -29,6 +29,9 @@ class SymmetryFunctionError(Exception):
 
 
 _DENSE_LIMIT_BYTES = 8 << 30
+# configurations up to this many atoms go through the batched all-pairs neighbor kernels (one CTA
+# per configuration); larger ones through the cell-list build
+_BATCH_MAX_ATOMS = 2048
 
 
 class SymmetryFunction(Descriptor):
@@ -108,8 +111,17 @@ class SymmetryFunction(Descriptor):
         device = device if device is not None else default_device()
         if not isinstance(configs, (list, tuple)):
             configs = [configs]
-        parts = [self._config_part(c, device)[0] for c in configs]
-        packed = PackedFingerprints.from_parts(len(self), device, parts)
+        if configs and max(c.get_num_atoms() for c in configs) <= _BATCH_MAX_ATOMS:
+            # many small cells: one CTA per configuration, 2 synchronisations for the whole list
+            try:
+                packed = PackedFingerprints.from_configs(len(self), device, configs, self.species_code,
+                                                         max(self.cutoff.values()))
+            except KeyError as e:
+                raise SymmetryFunctionError(f"species {e} not in the cutoff dictionary")
+        else:
+            # large cells: cell-list neighbor build per configuration
+            parts = [self._config_part(c, device)[0] for c in configs]
+            packed = PackedFingerprints.from_parts(len(self), device, parts)
         packed.compute(self._params, grad=grad, mode=self.kernel_mode,
                        dz_dtype=torch.float32 if gradient_dtype in (np.float32, torch.float32) else torch.float64)
         return packed

@@ -176,6 +176,49 @@ def build_neighbors(coords, n_need, infl_dist, cutoff=None, need=None, half=Fals
     return counts, offsets, indices, maxn.value
 
 
+def batch_neighbors(cfg_ptr, cells, pbcs, coords, cutoff):
+    """Paddings + neighbor lists of many configurations in one pass (kb_batch_*).
+
+    cfg_ptr: host int [C+1] contributing ranges into coords (cuda f64 [N,3]); cells: host
+    [C,3,3]; pbcs: host [C,3].  Returns dict(coords, image, centers, atom_ptr (host int64),
+    offsets, indices, maxn) in the packed batch layout (packed.py)."""
+    _need_cuda(coords)
+    coords = coords.contiguous()
+    if coords.dtype != torch.float64:
+        raise TypeError("coords must be float64")
+    cfg_ptr = np.ascontiguousarray(cfg_ptr, dtype=np.int32)
+    cells = np.ascontiguousarray(cells, dtype=np.float64).reshape(-1)
+    pbcs = np.ascontiguousarray(np.asarray(pbcs).astype(bool), dtype=np.int32).reshape(-1)
+    n_cfg = len(cfg_ptr) - 1
+    if len(cells) != 9 * n_cfg or len(pbcs) != 3 * n_cfg or int(cfg_ptr[-1]) != coords.shape[0]:
+        raise ValueError("batch_neighbors: inconsistent configuration arrays")
+    dev = coords.device
+    L = _lib.lib()
+    total_atoms, plan = C.c_int64(0), C.c_void_p(0)
+    check(L.kb_batch_begin(n_cfg, cfg_ptr.ctypes.data_as(C.c_void_p), cells.ctypes.data_as(C.c_void_p),
+                           pbcs.ctypes.data_as(C.c_void_p), float(cutoff), _ptr(coords),
+                           C.byref(total_atoms), C.byref(plan), _stream()), "kb_batch_begin")
+    A, N = total_atoms.value, coords.shape[0]
+    coords_all = torch.empty((A, 3), dtype=torch.float64, device=dev)
+    image = torch.empty((A,), dtype=torch.int32, device=dev)
+    centers = torch.empty((N,), dtype=torch.int32, device=dev)
+    atom_ptr = torch.empty((n_cfg + 1,), dtype=torch.int64, device=dev)
+    counts = torch.empty((A,), dtype=torch.int32, device=dev)
+    offsets = torch.zeros((A + 1,), dtype=torch.int64, device=dev)
+    pairs, maxn = C.c_int64(0), C.c_int32(0)
+    rc = L.kb_batch_neighbors(plan, _ptr(coords_all), _ptr(image), _ptr(centers), _ptr(atom_ptr),
+                              _ptr(counts), _ptr(offsets), C.byref(pairs), C.byref(maxn), _stream())
+    if rc != _lib.KB_OK:
+        L.kb_batch_destroy(plan, _stream())
+        check(rc, "kb_batch_neighbors")
+    indices = torch.empty((pairs.value,), dtype=torch.int32, device=dev)
+    check(L.kb_batch_finish(plan, _ptr(coords_all), _ptr(offsets), _ptr(indices), _stream()),
+          "kb_batch_finish")
+    return dict(coords=coords_all, image=image, centers=centers,
+                atom_ptr=atom_ptr.cpu().numpy() if n_cfg else np.zeros(1, np.int64),
+                offsets=offsets, indices=indices, maxn=maxn.value)
+
+
 # --------------------------------------------------------------------------- descriptor
 def block_offsets(n_centers, centers, offsets, n_desc):
     dev = offsets.device

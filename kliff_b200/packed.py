@@ -113,6 +113,32 @@ class PackedFingerprints:
         self.maxn = maxn
         return self
 
+    @classmethod
+    def from_configs(cls, D, device, configs, species_code, infl_dist):
+        """Batched assembly: paddings + neighbor lists of ALL configurations in one pass of the
+        kb_batch_* kernels (one CTA per configuration) instead of one NeighborList per
+        configuration (descriptor.py:186-238 loops `for conf in configs`)."""
+        self = cls(D, device)
+        sizes = np.asarray([c.get_num_atoms() for c in configs], np.int64)
+        cfg_ptr = np.zeros(len(configs) + 1, np.int64)
+        np.cumsum(sizes, out=cfg_ptr[1:])
+        n = int(cfg_ptr[-1])
+        coords = np.concatenate([np.asarray(c.coords, np.float64).reshape(-1, 3) for c in configs]) \
+            if n else np.zeros((0, 3))
+        code_cb = np.concatenate([np.asarray([species_code[s] for s in c.species], np.int32)
+                                  for c in configs]) if n else np.zeros(0, np.int32)
+        cells = np.stack([np.asarray(c.cell, np.float64).reshape(3, 3) for c in configs]) \
+            if len(configs) else np.zeros((0, 3, 3))
+        pbcs = np.stack([np.asarray(c.PBC).astype(bool) for c in configs]) if len(configs) else np.zeros((0, 3), bool)
+        d_coords = torch.as_tensor(coords, device=device)
+        out = ops.batch_neighbors(cfg_ptr, cells, pbcs, d_coords, infl_dist)
+        self.coords, self.image, self.centers = out["coords"], out["image"], out["centers"]
+        self.offsets, self.indices, self.maxn = out["offsets"], out["indices"], out["maxn"]
+        self.code = torch.as_tensor(code_cb, device=device)[self.image.long()]
+        self.atom_ptr = out["atom_ptr"].astype(np.int64)
+        self.cfg_ptr = cfg_ptr
+        return self
+
     def compute(self, params, grad=True, mode=0, dz_dtype=torch.float64):
         """Run the descriptor kernel over every centre atom (one launch)."""
         self.zeta, self.dz, self.dz_ptr = ops.symfun_forward(

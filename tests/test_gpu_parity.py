@@ -480,3 +480,90 @@ def test_random_differential(dev, port, seed):
         rs = np.abs(ref).reshape(D, -1).max(axis=1)
         err = np.abs(blk - ref).reshape(D, -1).max(axis=1)
         assert np.all(err <= TOL * np.maximum(rs, 1e-12)), (seed, t, float((err / np.maximum(rs, 1e-12)).max()))
+
+
+def _random_cell_config(rng, n_lo=1, n_hi=70):
+    cell = np.diag(rng.uniform(4.0, 11.0, 3)) + rng.normal(0, 0.7, (3, 3))
+    n = int(rng.integers(n_lo, n_hi))
+    pos = rng.random((n, 3)) @ cell
+    for _ in range(80):
+        if n < 2:
+            break
+        d = np.linalg.norm(pos[:, None] - pos[None], axis=-1) + np.eye(n) * 10
+        i, j = np.unravel_index(np.argmin(d), d.shape)
+        if d[i, j] > 0.8:
+            break
+        pos[j] += rng.normal(0, 0.8, 3)
+    return cell, pos, rng.integers(0, 2, 3)
+
+
+def test_batched_neighbors_bit_exact(dev, port):
+    """kb_batch_* (one CTA per configuration) against the oracle, configuration by configuration:
+    image-atom coordinates, owners, counts and neighbor indices all bit-exact.  Mix of random
+    triclinic cells / PBC flags, the reference's Si and SiC training cells, and an empty cell."""
+    from helpers import configs_from_npz
+    rng = np.random.default_rng(77)
+    items = [_random_cell_config(rng) for _ in range(40)]
+    for c in configs_from_npz("si_varying_alat.npz", limit=6) + configs_from_npz("sic_training_set.npz", limit=4):
+        items.append((np.asarray(c.cell, np.float64), np.asarray(c.coords, np.float64), np.asarray(c.PBC, int)))
+    items.insert(7, (np.eye(3) * 5.0, np.zeros((0, 3)), np.array([1, 1, 1])))  # no atoms at all
+    infl = 4.3
+    cfg_ptr = np.zeros(len(items) + 1, np.int64)
+    np.cumsum([len(p) for _, p, _ in items], out=cfg_ptr[1:])
+    coords = torch.tensor(np.concatenate([p for _, p, _ in items]), dtype=torch.float64, device=dev)
+    out = ops.batch_neighbors(cfg_ptr, np.stack([c for c, _, _ in items]),
+                              np.stack([b for _, _, b in items]), coords, infl)
+    ap = out["atom_ptr"]
+    gc, gi = out["coords"].cpu().numpy(), out["image"].cpu().numpy()
+    goff, gidx, gcen = out["offsets"].cpu().numpy(), out["indices"].cpu().numpy(), out["centers"].cpu().numpy()
+    maxn = 0
+    for c, (cell, pos, pbc) in enumerate(items):
+        n = len(pos)
+        a0, a1 = int(ap[c]), int(ap[c + 1])
+        if n == 0:
+            assert a0 == a1
+            continue
+        opc, _, opi = port.create_paddings(infl, cell, pbc, pos, np.full(n, 14, np.int32))
+        assert a1 - a0 == n + len(opc), f"config {c}: image count"
+        assert np.array_equal(gc[a0:a0 + n], pos)
+        assert np.array_equal(gc[a0 + n:a1], opc.reshape(-1, 3)), f"config {c}: image coordinates"
+        assert np.array_equal(gi[a0:a0 + n], cfg_ptr[c] + np.arange(n))
+        assert np.array_equal(gi[a0 + n:a1], cfg_ptr[c] + opi), f"config {c}: owners"
+        assert np.array_equal(gcen[cfg_ptr[c]:cfg_ptr[c + 1]], a0 + np.arange(n))
+        allc = np.concatenate([pos, opc.reshape(-1, 3)])
+        need = np.zeros(len(allc), np.int32)
+        need[:n] = 1
+        oc, oo, oi = port.build_neighbors(allc, infl, need)
+        oi = orc.canonical(oo, oi)
+        cnt = np.diff(goff[a0:a1 + 1])
+        assert np.array_equal(cnt, oc), f"config {c}: counts"
+        assert np.array_equal(gidx[goff[a0]:goff[a1]] - a0, oi), f"config {c}: indices"
+        maxn = max(maxn, int(oc.max()))
+    assert out["maxn"] == maxn
+    # errors: singular cell and colliding atoms are the reference's own failures
+    with pytest.raises(_lib.KliffB200Error):
+        ops.batch_neighbors([0, 1], np.zeros((1, 3, 3)), np.ones((1, 3)), coords[:1], infl)
+    two = torch.tensor([[0.0, 0, 0], [0, 0, 1e-7]], dtype=torch.float64, device=dev)
+    with pytest.raises(_lib.KliffB200Error):
+        ops.batch_neighbors([0, 2], np.eye(3)[None] * 6.0, np.ones((1, 3)), two, infl)
+
+
+def test_batched_descriptor_equals_per_configuration(dev):
+    """SymmetryFunction.transform_packed over a list (batched kernels) gives exactly what the
+    per-configuration cell-list path gives: same atoms, lists, zeta and gradient blocks."""
+    from helpers import configs_from_npz
+    from kliff_b200.legacy.descriptors import symmetry_function as sfm
+    from kliff_b200.legacy.descriptors.symmetry_function import SymmetryFunction
+    desc = SymmetryFunction({"Si-Si": 5.0, "Si-C": 4.5, "C-C": 4.0}, "cos", "set30")
+    confs = configs_from_npz("sic_training_set.npz", limit=5) + configs_from_npz("si_varying_alat.npz", limit=3)
+    a = desc.transform_packed(confs, grad=True, device=dev)
+    old = sfm._BATCH_MAX_ATOMS
+    sfm._BATCH_MAX_ATOMS = 0
+    try:
+        b = desc.transform_packed(confs, grad=True, device=dev)
+    finally:
+        sfm._BATCH_MAX_ATOMS = old
+    for name in ("coords", "code", "image", "offsets", "indices", "centers", "zeta", "dz", "dz_ptr"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert np.array_equal(a.atom_ptr, b.atom_ptr) and np.array_equal(a.cfg_ptr, b.cfg_ptr)
+    assert a.maxn == b.maxn
