@@ -81,7 +81,7 @@ __host__ __device__ inline size_t warp_smem_bytes(const kb_symfun_params& P, int
 {
   const int NG = P.n_groups, NT = P.n_two;
   size_t d = (size_t) 3 * NP + (size_t) NP * 8 + (size_t) RC * 4 + SC_DOUBLES + 4 * (size_t) NT
-             + (size_t) P.n_species * P.n_species;
+             + (size_t) P.n_species * P.n_species + 64;
   size_t bytes = d * 8 + (size_t) NP * 8;        // + adjacency masks
   bytes += (size_t) NP * 8;                      // species, record base
   bytes += (size_t) (NP * NP + RC) * 2;          // per-slot record lists, pair list
@@ -106,7 +106,8 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
   double* SC = RK + RC * SR;                          // [32][SCW]
   double* Z2 = SC + SC_DOUBLES;                       // [NT] radial zeta, [3 NT] radial centre slot
   double* RCI = Z2 + 4 * NT;                          // [S][S] 1 / rc
-  unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(RCI + S * S);  // [NP]
+  double* TAB = RCI + S * S;                          // [64] 2^(j/64) for kb_exp_tab
+  unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(TAB + 64);  // [NP]
   int* SPC = reinterpret_cast<int*>(ADJ + NP);        // [NP]
   int* BASE = SPC + NP;                               // [NP] first record slot of row j (pairs j<k)
   unsigned short* JR = reinterpret_cast<unsigned short*>(BASE + NP);   // [NP][NP] record of (slot, idx)
@@ -131,6 +132,8 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
   }
   const double p2tab[GW] = {1.0, 1.0, 0.5, 0.5, 0.125, 0.125, 1.0 / 32768.0, 1.0 / 32768.0};
   for (int q = lane; q < S * S; q += 32) RCI[q] = 1.0 / P.rcut[q];
+  kb_exp_table_fill(TAB, lane);
+  for (int q = lane; q < SC_DOUBLES; q += 32) SC[q] = 0.0;  // empty scratch entries must be finite
   __syncwarp();
 
   for (;;)
@@ -323,9 +326,39 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
     __syncwarp();
 
     // ---- phase E: triple loop -------------------------------------------------------------------
-    double csum[GW][3], zsum[GW];
+    // csum: centre-slot partial sums; phi: zeta partial sums (both carried across the atom's items)
+    double csum[GW][3], phi[GW];
 #pragma unroll
-    for (int e = 0; e < GW; e++) { csum[e][0] = csum[e][1] = csum[e][2] = 0.0; zsum[e] = 0.0; }
+    for (int e = 0; e < GW; e++) { csum[e][0] = csum[e][1] = csum[e][2] = 0.0; phi[e] = 0.0; }
+
+    // one sweep step: every eta-lane folds scratch entry `sc` of its slot into its accumulators.
+    // Entries beyond a slot's list are all-zero (F = 0, vectors = 0), so the step needs no predicate.
+    double acc[GW][3];
+    auto sweep_step = [&](const double* sc) {
+      const double F = sc[1];
+      const double E = kb_exp_tab(-eta * sc[11], TAB);  // e^{-eta (rij^2 + rik^2 + rjk^2)}, :770
+      const double eF = E * F, Ee = E * eta;
+      const double v1x = eF * sc[2], v1y = eF * sc[3], v1z = eF * sc[4];
+      const double v2x = fma(Ee, sc[5], E * sc[8]), v2y = fma(Ee, sc[6], E * sc[9]),
+                   v2z = fma(Ee, sc[7], E * sc[10]);
+#pragma unroll
+      for (int e = 0; e < GW; e += 2)
+      {
+        const double2 c2 = *reinterpret_cast<const double2*>(sc + 12 + e);
+        const double2 d2 = *reinterpret_cast<const double2*>(sc + 20 + e);
+        phi[e] = fma(c2.x, eF, phi[e]);
+        phi[e + 1] = fma(c2.y, eF, phi[e + 1]);
+        if (GRAD)
+        {
+          acc[e][0] = fma(c2.x, v2x, fma(d2.x, v1x, acc[e][0]));
+          acc[e][1] = fma(c2.x, v2y, fma(d2.x, v1y, acc[e][1]));
+          acc[e][2] = fma(c2.x, v2z, fma(d2.x, v1z, acc[e][2]));
+          acc[e + 1][0] = fma(c2.y, v2x, fma(d2.y, v1x, acc[e + 1][0]));
+          acc[e + 1][1] = fma(c2.y, v2y, fma(d2.y, v1y, acc[e + 1][1]));
+          acc[e + 1][2] = fma(c2.y, v2z, fma(d2.y, v1z, acc[e + 1][2]));
+        }
+      }
+    };
 
     const int nwi = (n + KPW - 1) / KPW;
     for (int wi = 0; wi < nwi; wi++)
@@ -333,33 +366,32 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       const int kk = wi * KPW + ksub;
       const bool valid_k = kk < n;
       const int k = valid_k ? KORD[kk] : 0;
-      const double* tk = TJ + k * SJ;
-      const double rik = tk[0], rik2 = tk[1], irik = tk[2], fik = tk[3], dfik = tk[4];
-      const double ukx = tk[5], uky = tk[6], ukz = tk[7];
-      const double xk = XYZ[k], yk = XYZ[NP + k], zk = XYZ[2 * NP + k];
       const int degk = valid_k ? DEG[k] : 0;
       const int maxdeg = __reduce_max_sync(FULL, degk);
-      const unsigned char* jl = JL + k * NP;
-      const unsigned short* jr = JR + k * NP;
       double* scg = SC + ksub * (NGP * SCW + 2);  // this slot's scratch group
 
-      double acc[GW][3], phi[GW];
 #pragma unroll
-      for (int e = 0; e < GW; e++) { acc[e][0] = acc[e][1] = acc[e][2] = 0.0; phi[e] = 0.0; }
+      for (int e = 0; e < GW; e++) acc[e][0] = acc[e][1] = acc[e][2] = 0.0;
 
       for (int s0 = 0; s0 < maxdeg; s0 += NGP)
       {
-        // geometry of up to NGP ordered pairs (j -> k) per slot: lane g takes list entry s0 + g
+        // geometry of up to NGP ordered pairs (j -> k) per slot: lane g takes list entry s0 + g.
+        // The slot's own constants are re-read from shared memory here (not kept in registers
+        // across the sweep below, where every register is needed for accumulators).
+        double* sc = scg + g * SCW;
         if (s0 + g < degk)
         {
-          const int j = jl[s0 + g];
-          const int rec = jr[s0 + g];
+          const double* tk = TJ + k * SJ;
+          const double rik = tk[0], rik2 = tk[1], irik = tk[2], fik = tk[3], dfik = tk[4];
+          const double ukx = tk[5], uky = tk[6], ukz = tk[7];
+          const int j = JL[k * NP + s0 + g];
+          const int rec = JR[k * NP + s0 + g];
           const double* tj = TJ + j * SJ;
           const double* rk = RK + rec * SR;
           const double rij2 = tj[1], irij = tj[2], fij = tj[3];
           const double rjk = rk[0], irjk = rk[1], fjk = rk[2], dfjk = rk[3];
-          const double wx = (xk - XYZ[j]) * irjk, wy = (yk - XYZ[NP + j]) * irjk,
-                       wz = (zk - XYZ[2 * NP + j]) * irjk;      // unit vector j -> k
+          const double wx = (XYZ[k] - XYZ[j]) * irjk, wy = (XYZ[NP + k] - XYZ[NP + j]) * irjk,
+                       wz = (XYZ[2 * NP + k] - XYZ[2 * NP + j]) * irjk;      // unit vector j -> k
           const double rjk2 = rjk * rjk;
           const double h = 0.5 * irij * irik;
           const double ct = (rij2 + rik2 - rjk2) * h;            // cos(theta_jik), :744
@@ -369,8 +401,6 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
           const double F = fijk * fik;
           const double dF_ik = dfik * fijk, dF_jk = dfjk * (fij * fik);
           const double a = -2.0 * F * rik, b = -2.0 * F * rjk;
-          double* sc = scg + g * SCW;
-          sc[0] = ct;
           sc[1] = F;
           sc[2] = dct_ik * ukx + dct_jk * wx; sc[3] = dct_ik * uky + dct_jk * wy; sc[4] = dct_ik * ukz + dct_jk * wz;
           sc[5] = a * ukx + b * wx;           sc[6] = a * uky + b * wy;           sc[7] = a * ukz + b * wz;
@@ -393,62 +423,40 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
             sc[12 + 6 + si2] = b16; sc[20 + 6 + si2] = 16.0 * lam * b15;
           }
         }
-        const int left = degk - s0;
-        const int cnt = left < 0 ? 0 : (left < NGP ? left : NGP);
-        const int maxcnt = __reduce_max_sync(FULL, cnt);
+        else
+        {
+          // empty entry: contributes exactly zero (its C / C' words are finite leftovers or the
+          // zeros the scratch was initialised with)
+#pragma unroll
+          for (int q = 1; q < 12; q++) sc[q] = 0.0;
+        }
+        const int left = maxdeg - s0;
+        const int maxcnt = left < NGP ? left : NGP;  // warp-uniform
         __syncwarp();
 
-        for (int ej = 0; ej < maxcnt; ej++)
+        int ej = 0;
+#pragma unroll 1
+        for (; ej + 1 < maxcnt; ej += 2)
         {
-          if (ej < cnt && valid_g)
-          {
-            const double* sc = scg + ej * SCW;
-            const double ct = sc[0], F = sc[1];
-            const double E = kb_exp_neg(-eta * sc[11]);  // e^{-eta (rij^2 + rik^2 + rjk^2)}, :770
-            const double eF = E * F, Ee = E * eta;
-            const double v1x = eF * sc[2], v1y = eF * sc[3], v1z = eF * sc[4];
-            const double v2x = fma(Ee, sc[5], E * sc[8]), v2y = fma(Ee, sc[6], E * sc[9]),
-                         v2z = fma(Ee, sc[7], E * sc[10]);
-            double C[GW], Cp[GW];
-#pragma unroll
-            for (int e = 0; e < GW; e += 2)
-            {
-              const double2 c2 = *reinterpret_cast<const double2*>(sc + 12 + e);
-              const double2 d2 = *reinterpret_cast<const double2*>(sc + 20 + e);
-              C[e] = c2.x; C[e + 1] = c2.y; Cp[e] = d2.x; Cp[e + 1] = d2.y;
-            }
-#pragma unroll
-            for (int e = 0; e < GW; e++)
-            {
-              phi[e] = fma(C[e], eF, phi[e]);
-              if (GRAD)
-              {
-                acc[e][0] = fma(C[e], v2x, fma(Cp[e], v1x, acc[e][0]));
-                acc[e][1] = fma(C[e], v2y, fma(Cp[e], v1y, acc[e][1]));
-                acc[e][2] = fma(C[e], v2z, fma(Cp[e], v1z, acc[e][2]));
-              }
-            }
-          }
+          sweep_step(scg + ej * SCW);
+          sweep_step(scg + (ej + 1) * SCW);
         }
+        if (ej < maxcnt) sweep_step(scg + ej * SCW);
         __syncwarp();
       }
 
-      // item done: write slot k's rows, fold into the per-atom partial sums
-      if (valid_k && valid_g)
+      // item done: write slot k's rows, fold into the centre-slot partial sums
+      if (GRAD && valid_k && valid_g)
       {
 #pragma unroll
         for (int e = 0; e < GW; e++)
         {
-          zsum[e] += phi[e];
-          if (GRAD)
+          csum[e][0] += acc[e][0]; csum[e][1] += acc[e][1]; csum[e][2] += acc[e][2];
+          if (gout[e] >= 0)
           {
-            csum[e][0] += acc[e][0]; csum[e][1] += acc[e][1]; csum[e][2] += acc[e][2];
-            if (gout[e] >= 0)
-            {
-              TOut* o = blk + (int64_t) gout[e] * row + 3 * k;
-              o[0] = (TOut) (p2tab[e] * acc[e][0]); o[1] = (TOut) (p2tab[e] * acc[e][1]);
-              o[2] = (TOut) (p2tab[e] * acc[e][2]);
-            }
+            TOut* o = blk + (unsigned) (gout[e] * row + 3 * k);
+            o[0] = (TOut) (p2tab[e] * acc[e][0]); o[1] = (TOut) (p2tab[e] * acc[e][1]);
+            o[2] = (TOut) (p2tab[e] * acc[e][2]);
           }
         }
       }
@@ -460,7 +468,7 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
     {
       for (int m = NGP; m < 32; m <<= 1)
       {
-        zsum[e] += shfl_xor_d(zsum[e], m);
+        phi[e] += shfl_xor_d(phi[e], m);
         if (GRAD)
         {
           csum[e][0] += shfl_xor_d(csum[e][0], m);
@@ -470,10 +478,10 @@ symfun_warp_kernel(const __grid_constant__ kb_symfun_params P, const WarpArgs A)
       }
       if (ksub == 0 && gout[e] >= 0)
       {
-        zrow[gout[e]] = 0.5 * p2tab[e] * zsum[e];  // each unordered triple was visited twice
+        zrow[gout[e]] = 0.5 * p2tab[e] * phi[e];  // each unordered triple was visited twice
         if (GRAD)
         {
-          TOut* o = blk + (int64_t) gout[e] * row + 3 * n;
+          TOut* o = blk + (unsigned) (gout[e] * row + 3 * n);
           o[0] = (TOut) (-p2tab[e] * csum[e][0]); o[1] = (TOut) (-p2tab[e] * csum[e][1]);
           o[2] = (TOut) (-p2tab[e] * csum[e][2]);
         }
