@@ -176,6 +176,7 @@ void kb_batch_destroy(kb_batch_plan* plan, void* stream);
 #define KB_SYMFUN_GENERAL 1     /* global-atomics kernel: any neighbor count */
 #define KB_SYMFUN_TILED 2       /* CTA-per-atom shared-memory kernel: n <= 64, any families */
 #define KB_SYMFUN_WARP 3        /* warp-per-atom kernel: n <= 64, g1-g4 with zeta in {1,2,4,16}, lambda = +-1 */
+#define KB_SYMFUN_SPLIT 4       /* same domain as WARP, two launches: table kernel + triple-sweep kernel (AUTO's first choice) */
 
 int kb_symfun_block_offsets(int32_t n_centers, const int32_t* d_centers,
                             const int64_t* d_nl_offsets, int32_t n_desc, int64_t* d_dz_ptr,

@@ -87,3 +87,23 @@ __device__ __forceinline__ double warp_reduce32(double (&v)[32], int lane)
   }
   return v[0];
 }
+
+// 16-value variant (fewer live registers): on return lane l holds the warp-wide total of v[l & 15].
+__device__ __forceinline__ double warp_reduce16(double (&v)[16], int lane)
+{
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] += shfl_xor_d(v[i], 16);
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1)
+  {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; i++)
+    {
+      const double keep = upper ? v[i + half] : v[i];
+      const double send = upper ? v[i] : v[i + half];
+      v[i] = keep + shfl_xor_d(send, half);
+    }
+  }
+  return v[0];
+}

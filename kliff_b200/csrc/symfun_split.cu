@@ -1,0 +1,694 @@
+// Two-stage form of the warp-per-atom symmetry-function kernel (symfun_warp.cu): the hot path, v3.
+//
+// ncu on the fused kernel (profiles/r01_ncu_symfun_warp_v3.txt) shows where its time goes: the FMA
+// sweep over neighbor triples keeps the FP64 pipe ~78 % busy, but it is only a third of the run;
+// the table phases before it (pair-ij table, radial sets, adjacency rows, pair-jk records, slot
+// sort) are chains of dependent shared-memory round trips that issue one instruction every ~7
+// cycles, and with 242 registers per thread only 8 warps fit on an SM to hide that.  So the two
+// halves want opposite launch shapes, and here they get them:
+//
+//   symfun_prep_kernel   ~100 registers, 2.5-5 KB of shared memory per warp -> 5x the resident warps.
+//                        Per atom: phases A, D, B, C, S of symfun_warp.cu (same arithmetic, same
+//                        order), radial rows of dG/dr written to their final place, and the tables
+//                        the sweep needs packed into one "atom record" in global memory.
+//   symfun_sweep_kernel  persistent, 8+ warps per SM, one atom per warp at a time: copies the record
+//                        (~10 KB, one coalesced pass) into shared memory and runs only the triple
+//                        loop (phases E, F) — the part that is FP64-pipe bound.
+//
+// Atoms are processed in chunks so that the records of a chunk (stride ~17 KB per atom for n <= 28)
+// stay a bounded scratch allocation; the extra HBM traffic is ~2 x 10 KB per atom on top of the 37 KB
+// block itself, on a kernel that uses ~13 % of the HBM bandwidth.
+//
+// Reference: Descriptor::generate_one_atom (sym_fn.cpp:416-602), sym_d_g2 / sym_d_g4 (:627-809).
+#include "common.cuh"
+#include "symfun_math.cuh"
+
+#include <cstdlib>
+
+namespace {
+
+constexpr int GW = KB_GROUP_WIDTH;
+constexpr int SCW = 28;  // doubles per scratch entry: 12 geometry + 8 C + 8 C'
+constexpr int SC_DOUBLES = 32 * SCW + 2 * 32;
+constexpr int SJ = 8, SR = 4;
+constexpr int PREP_WARPS = 4;
+
+#ifndef KB_SWEEP_MIN_BLOCKS
+#define KB_SWEEP_MIN_BLOCKS 8
+#endif
+#ifndef KB_SWEEP_MIN_BLOCKS_NOGRAD
+#define KB_SWEEP_MIN_BLOCKS_NOGRAD 12
+#endif
+#ifndef KB_PREP_MIN_BLOCKS
+#define KB_PREP_MIN_BLOCKS 6  // 80 registers: 24 resident warps per SM, no spills
+#endif
+
+// ---- the atom record (global memory and, byte for byte, the head of the sweep warp's shared memory)
+struct RecLayout
+{
+  int kord, deg, xyz, tj, jl, jr, rk, bytes;  // byte offsets; header int32 {n, nrec, -, -} at 0
+};
+__host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline RecLayout rec_layout(int NP, int RC)
+{
+  RecLayout L;
+  L.kord = 16;
+  L.deg = 16 + NP;
+  int o = al16(16 + 2 * NP);
+  L.xyz = o; o += 24 * NP;        // [3][NP] doubles
+  L.tj = o;  o += 64 * NP;        // [NP][8]: r r2 1/r fc dfc ux uy uz
+  L.jl = o;  o = al16(o + NP * NP);      // [NP][NP] u8: idx-th adjacent neighbor of slot k
+  L.jr = o;  o = al16(o + 2 * NP * NP);  // [NP][NP] u16: its pair-jk record
+  L.rk = o;  o += 32 * RC;        // [nrec][4]: r 1/r fc dfc
+  L.bytes = al16(o);
+  return L;
+}
+
+struct SplitArgs
+{
+  int lo, hi;  // centre ordinals [lo, hi) of this chunk
+  const int32_t* centers;
+  const int32_t* subset;
+  const double* coords;
+  const int32_t* species;
+  const int64_t* nl_off;
+  const int32_t* nl_idx;
+  double* zeta;
+  void* dz;
+  const int64_t* dz_ptr;
+  int32_t* overflow;      // [0] count, [2..] declined ordinals
+  int32_t* work;          // sweep: dynamic work counter of this chunk
+  unsigned char* records; // [hi - lo] records
+  int NP, RC, NGP;
+};
+
+__host__ __device__ inline size_t prep_smem_bytes(const kb_symfun_params& P, int NP, int RC)
+{
+  size_t b = (size_t) 24 * NP + 32 * (size_t) P.n_two + 8 * (size_t) P.n_species * P.n_species;
+  b += (size_t) 8 * NP + 4 * NP + 4 * NP;           // ADJ, SPC, BASE
+  b = (b + 15) & ~(size_t) 15;
+  b += al16(2 * NP * NP) + al16(NP * NP);           // JR, JL (copied out as 16-byte words)
+  b += (size_t) 2 * RC + 2 * (size_t) NP;           // PAIR, DEG + KORD
+  return (b + 15) & ~(size_t) 15;
+}
+
+// =============================================================================================
+// stage 1: tables
+// =============================================================================================
+template <bool GRAD, typename TOut>
+__global__ void __launch_bounds__(PREP_WARPS * 32, KB_PREP_MIN_BLOCKS)
+symfun_prep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A, const int warp_bytes)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned FULL = 0xffffffffu;
+  const int NP = A.NP, RC = A.RC, D = P.n_desc, NT = P.n_two, S = P.n_species;
+  const RecLayout L = rec_layout(NP, RC);
+
+  unsigned char* base = smem_raw + (size_t) warp * warp_bytes;
+  double* XYZ = reinterpret_cast<double*>(base);      // [3][NP]
+  double* Z2 = XYZ + 3 * NP;                          // [NT] radial zeta, [3 NT] radial centre slot
+  double* RCI = Z2 + 4 * NT;                          // [S][S] 1 / rc
+  unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(RCI + S * S);  // [NP]
+  int* SPC = reinterpret_cast<int*>(ADJ + NP);        // [NP]
+  int* BASE = SPC + NP;                               // [NP]
+  unsigned char* p = reinterpret_cast<unsigned char*>(BASE + NP);
+  p = base + al16((int) (p - base));
+  unsigned short* JR = reinterpret_cast<unsigned short*>(p);  p += al16(2 * NP * NP);
+  unsigned char* JL = p;                                      p += al16(NP * NP);
+  unsigned short* PAIR = reinterpret_cast<unsigned short*>(p);  // [RC]
+  unsigned char* DEG = reinterpret_cast<unsigned char*>(PAIR + RC);  // [NP]
+  unsigned char* KORD = DEG + NP;                                     // [NP]
+
+  for (int q = lane; q < S * S; q += 32) RCI[q] = 1.0 / P.rcut[q];
+  __syncwarp();
+
+  const int stride = gridDim.x * PREP_WARPS;
+  for (int tt = A.lo + blockIdx.x * PREP_WARPS + warp; tt < A.hi; tt += stride)
+  {
+    const int t = A.subset ? A.subset[tt] : tt;
+    unsigned char* rec = A.records + (size_t) (tt - A.lo) * L.bytes;
+    int* hdr = reinterpret_cast<int*>(rec);
+    const int i = A.centers ? A.centers[t] : t;
+    const int64_t off = A.nl_off[i];
+    const int n = (int) (A.nl_off[i + 1] - off);
+    if (n > NP)
+    {
+      if (lane == 0) { A.overflow[2 + atomicAdd(A.overflow, 1)] = t; hdr[0] = -1; hdr[1] = 0; }
+      continue;
+    }
+    const int si = A.species[i];
+    const double xi = A.coords[3 * i], yi = A.coords[3 * i + 1], zi = A.coords[3 * i + 2];
+    const int row = 3 * (n + 1);
+    TOut* blk = GRAD ? static_cast<TOut*>(A.dz) + A.dz_ptr[t] : nullptr;
+    double* zrow = A.zeta + (int64_t) t * D;
+    double* gXYZ = reinterpret_cast<double*>(rec + L.xyz);
+    double* gTJ = reinterpret_cast<double*>(rec + L.tj);
+    double* gRK = reinterpret_cast<double*>(rec + L.rk);
+
+    __syncwarp();
+    for (int q = lane; q < 4 * NT; q += 32) Z2[q] = 0.0;
+    __syncwarp();
+
+    // ---- phases A + D: pair-ij table and radial sets; lanes = neighbors ----------------------
+    unsigned long long ACT = 0ull;
+    for (int j0 = 0; j0 < n; j0 += 32)
+    {
+      const int jj = j0 + lane;
+      bool act = false;
+      double r = 1.0, fc = 0.0, dfc = 0.0, ux = 0.0, uy = 0.0, uz = 0.0;
+      if (jj < n)
+      {
+        const int j = A.nl_idx[off + jj];
+        const int sj = A.species[j];
+        const double xj = A.coords[3 * j], yj = A.coords[3 * j + 1], zj = A.coords[3 * j + 2];
+        const double vx = xsub(xj, xi), vy = xsub(yj, yi), vz = xsub(zj, zi);
+        const double r2x = xnorm2(vx, vy, vz);
+        r = sqrt(r2x);                  // sym_fn.cpp:447-448
+        const double rc = P.rcut[si * S + sj];
+        act = !(r > rc);                // :451
+        const double ir = rsqrt(r2x);
+        kb_cutoff_fast(r, rc, RCI[si * S + sj], fc, dfc);
+        if (!act) { fc = 0.0; dfc = 0.0; }
+        ux = vx * ir; uy = vy * ir; uz = vz * ir;
+        XYZ[jj] = xj; XYZ[NP + jj] = yj; XYZ[2 * NP + jj] = zj;
+        gXYZ[jj] = xj; gXYZ[NP + jj] = yj; gXYZ[2 * NP + jj] = zj;
+        SPC[jj] = sj;
+        double2* tj = reinterpret_cast<double2*>(gTJ + jj * SJ);
+        tj[0] = make_double2(r, r2x); tj[1] = make_double2(ir, fc);
+        tj[2] = make_double2(dfc, ux); tj[3] = make_double2(uy, uz);
+      }
+      ACT |= (unsigned long long) __ballot_sync(FULL, act) << j0;
+      for (int q0 = 0; q0 < NT; q0 += 4)
+      {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 4; u++)  // 4 independent radial sets per trip
+        {
+          const int q = q0 + u;
+          double phi = 0.0, dphi = 0.0;
+          if (q < NT && act) kb_radial(P.two_kind[q], P.two_p0[q], P.two_p1[q], r, fc, dfc, phi, dphi);
+          const double px = dphi * ux, py = dphi * uy, pz = dphi * uz;  // :497
+          if (GRAD && q < NT && jj < n)
+          {
+            TOut* o = blk + (unsigned) (P.two_out[q] * row + 3 * jj);
+            o[0] = (TOut) px; o[1] = (TOut) py; o[2] = (TOut) pz;
+          }
+          v[4 * u] = phi; v[4 * u + 1] = px; v[4 * u + 2] = py; v[4 * u + 3] = pz;
+        }
+        const double tot = warp_reduce16(v, lane);  // lanes 0-15: total of value (set l/4, component l%4)
+        const int q = q0 + ((lane & 15) >> 2), comp = lane & 3;
+        if (q < NT && lane < 16)
+        {
+          if (comp == 0) Z2[q] += tot;
+          else Z2[NT + 3 * q + comp - 1] += tot;
+        }
+      }
+    }
+    __syncwarp();
+    for (int q = lane; q < NT; q += 32)
+    {
+      zrow[P.two_out[q]] = Z2[q];
+      if (GRAD)
+      {
+        TOut* o = blk + (unsigned) (P.two_out[q] * row + 3 * n);  // centre slot, :499-501
+        o[0] = (TOut) -Z2[NT + 3 * q]; o[1] = (TOut) -Z2[NT + 3 * q + 1]; o[2] = (TOut) -Z2[NT + 3 * q + 2];
+      }
+    }
+
+    // ---- phase B: adjacency rows (reference predicate r_jk <= rc_jk, sym_fn.cpp:729) ------------
+    int nrec = 0;
+    for (int j0 = 0; j0 < n; j0 += 32)
+    {
+      const int j = j0 + lane;
+      unsigned long long mask = 0ull;
+      if (j < n && ((ACT >> j) & 1ull))
+      {
+        const double xj = XYZ[j], yj = XYZ[NP + j], zj = XYZ[2 * NP + j];
+        const double* rcrow = P.rcut + SPC[j] * S;
+        for (int k = 0; k < n; k++)
+        {
+          const double r2 = xnorm2(xsub(XYZ[k], xj), xsub(XYZ[NP + k], yj), xsub(XYZ[2 * NP + k], zj));
+          const double rc = rcrow[SPC[k]];
+          const double rc2 = rc * rc;
+          bool hit = r2 < rc2 * (1.0 - 1e-12);
+          if (!hit && r2 <= rc2 * (1.0 + 1e-12)) hit = !(sqrt(r2) > rc);
+          if (hit && k != j && ((ACT >> k) & 1ull)) mask |= 1ull << k;
+        }
+      }
+      const int upper = (j < 63) ? __popcll(mask >> (j + 1)) : 0;
+      int inc = upper;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const int y = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += y;
+      }
+      if (j < n)
+      {
+        ADJ[j] = mask;
+        DEG[j] = (unsigned char) __popcll(mask);
+        BASE[j] = nrec + inc - upper;
+      }
+      nrec += __shfl_sync(FULL, inc, 31);
+    }
+    if (nrec > RC)
+    {
+      if (lane == 0) { A.overflow[2 + atomicAdd(A.overflow, 1)] = t; hdr[0] = -1; hdr[1] = 0; }
+      continue;
+    }
+    __syncwarp();
+    for (int k = lane; k < n; k += 32)
+    {
+      unsigned long long m = ADJ[k];
+      int idx = 0;
+      while (m)
+      {
+        const int j = __ffsll((long long) m) - 1;
+        m &= m - 1ull;
+        const int a = j < k ? j : k, b = j < k ? k : j;
+        const unsigned long long between = (ADJ[a] >> (a + 1)) & ((1ull << (b - a - 1)) - 1ull);
+        const int slot = BASE[a] + __popcll(between);
+        JL[k * NP + idx] = (unsigned char) j;
+        JR[k * NP + idx] = (unsigned short) slot;
+        if (j > k) PAIR[slot] = (unsigned short) (k | (j << 8));
+        idx++;
+      }
+    }
+    __syncwarp();
+
+    // ---- phase C: pair-jk records; lanes = records, two per trip ---------------------------------
+    for (int r0 = lane; r0 < nrec; r0 += 64)
+    {
+      const int r1 = r0 + 32;
+      const bool two = r1 < nrec;
+      const int ja = PAIR[r0] & 0xff, ka = PAIR[r0] >> 8;
+      const int pb = two ? PAIR[r1] : PAIR[r0];
+      const int jb = pb & 0xff, kb = pb >> 8;
+      const double r2a = xnorm2(xsub(XYZ[ka], XYZ[ja]), xsub(XYZ[NP + ka], XYZ[NP + ja]),
+                                xsub(XYZ[2 * NP + ka], XYZ[2 * NP + ja]));
+      const double r2b = xnorm2(xsub(XYZ[kb], XYZ[jb]), xsub(XYZ[NP + kb], XYZ[NP + jb]),
+                                xsub(XYZ[2 * NP + kb], XYZ[2 * NP + jb]));
+      const double ra = sqrt(r2a), rb = sqrt(r2b);
+      const double ira = rsqrt(r2a), irb = rsqrt(r2b);
+      double fca, dfca, fcb, dfcb;
+      const int pa = SPC[ja] * S + SPC[ka], pb2 = SPC[jb] * S + SPC[kb];
+      kb_cutoff_fast(ra, P.rcut[pa], RCI[pa], fca, dfca);
+      kb_cutoff_fast(rb, P.rcut[pb2], RCI[pb2], fcb, dfcb);
+      double2* rka = reinterpret_cast<double2*>(gRK + r0 * SR);
+      rka[0] = make_double2(ra, ira); rka[1] = make_double2(fca, dfca);
+      if (two)
+      {
+        double2* rkb = reinterpret_cast<double2*>(gRK + r1 * SR);
+        rkb[0] = make_double2(rb, irb); rkb[1] = make_double2(fcb, dfcb);
+      }
+    }
+
+    // ---- phase S: slots ordered by adjacency degree (descending, index as tie-break) ---------
+    for (int k = lane; k < n; k += 32)
+    {
+      const int dk = DEG[k];
+      int rank = 0;
+      for (int m = 0; m < n; m++) rank += (DEG[m] > dk) || (DEG[m] == dk && m < k);
+      KORD[rank] = (unsigned char) k;
+    }
+    __syncwarp();
+
+    // ---- record: lists, order, header ----------------------------------------------------------
+    {
+      const uint4* s4 = reinterpret_cast<const uint4*>(JL);
+      uint4* g4 = reinterpret_cast<uint4*>(rec + L.jl);
+      for (int q = lane; q < al16(NP * NP) / 16; q += 32) g4[q] = s4[q];
+      s4 = reinterpret_cast<const uint4*>(JR);
+      g4 = reinterpret_cast<uint4*>(rec + L.jr);
+      for (int q = lane; q < al16(2 * NP * NP) / 16; q += 32) g4[q] = s4[q];
+      for (int q = lane; q < n; q += 32) { rec[L.kord + q] = KORD[q]; rec[L.deg + q] = DEG[q]; }
+      if (lane == 0) { hdr[0] = n; hdr[1] = nrec; }
+    }
+  }
+}
+
+// =============================================================================================
+// stage 2: triple sweep
+// =============================================================================================
+template <bool GRAD, typename TOut>
+__global__ void __launch_bounds__(32, GRAD ? KB_SWEEP_MIN_BLOCKS : KB_SWEEP_MIN_BLOCKS_NOGRAD)
+symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const unsigned FULL = 0xffffffffu;
+  const int NP = A.NP, NG = P.n_groups, NGP = A.NGP, D = P.n_desc;
+  const RecLayout L = rec_layout(NP, A.RC);
+
+  const unsigned char* KORD = smem_raw + L.kord;
+  const unsigned char* DEG = smem_raw + L.deg;
+  const double* XYZ = reinterpret_cast<const double*>(smem_raw + L.xyz);
+  const double* TJ = reinterpret_cast<const double*>(smem_raw + L.tj);
+  const unsigned char* JL = smem_raw + L.jl;
+  const unsigned short* JR = reinterpret_cast<const unsigned short*>(smem_raw + L.jr);
+  const double* RK = reinterpret_cast<const double*>(smem_raw + L.rk);
+  double* SC = reinterpret_cast<double*>(smem_raw + L.bytes);  // [32][SCW] (+ padding)
+  double* TAB = SC + SC_DOUBLES;                               // [64] 2^(j/64)
+
+  const int KPW = 32 / NGP;
+  const int ksub = lane / NGP, g = lane & (NGP - 1);
+  const bool valid_g = g < NG;
+  double eta = 0.0;
+  int gout[GW];
+#pragma unroll
+  for (int e = 0; e < GW; e++) gout[e] = -1;
+  if (valid_g)
+  {
+    eta = P.grp_eta[g];
+#pragma unroll
+    for (int e = 0; e < GW; e++) gout[e] = P.grp_out[g][e];
+  }
+  const double p2tab[GW] = {1.0, 1.0, 0.5, 0.5, 0.125, 0.125, 1.0 / 32768.0, 1.0 / 32768.0};
+  kb_exp_table_fill(TAB, lane);
+  for (int q = lane; q < SC_DOUBLES; q += 32) SC[q] = 0.0;  // empty scratch entries must be finite
+  __syncwarp();
+
+  // work distribution: one atom per grab, taken one atom AHEAD so that the next record can be pulled
+  // into L2 while the current atom is swept
+  int tt_next = 0;
+  if (lane == 0) tt_next = A.lo + atomicAdd(A.work, 1);
+  tt_next = __shfl_sync(FULL, tt_next, 0);
+  for (;;)
+  {
+    const int tt = tt_next;
+    if (tt >= A.hi) break;
+    if (lane == 0) tt_next = A.lo + atomicAdd(A.work, 1);
+    tt_next = __shfl_sync(FULL, tt_next, 0);
+    const int t = A.subset ? A.subset[tt] : tt;
+    const unsigned char* rec = A.records + (size_t) (tt - A.lo) * L.bytes;
+    const int4 hdr = __ldcg(reinterpret_cast<const int4*>(rec));
+    const int n = hdr.x, nrec = hdr.y;
+    if (tt_next < A.hi)
+    {
+      // the lists / tables part of the next record (its pair records follow at L.rk; their count is
+      // not known yet, fetch the typical half of the capacity)
+      const unsigned char* nx = A.records + (size_t) (tt_next - A.lo) * L.bytes;
+      const int lines = (L.rk + 16 * A.RC + 127) >> 7;
+      for (int q = lane; q < lines; q += 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + ((size_t) q << 7)));
+    }
+    if (n < 0) continue;  // declined by stage 1
+    __syncwarp();
+    {
+      // record -> shared memory with asynchronous 16-byte copies: all of them in flight at once
+      const int words = (L.rk + 32 * nrec) >> 4;
+      const unsigned sbase = (unsigned) __cvta_generic_to_shared(smem_raw);
+      for (int q = lane; q < words; q += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * q), "l"(rec + 16 * (size_t) q) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    const int row = 3 * (n + 1);
+    TOut* blk = GRAD ? static_cast<TOut*>(A.dz) + A.dz_ptr[t] : nullptr;
+    double* zrow = A.zeta + (int64_t) t * D;
+    __syncwarp();
+
+    // ---- phase E: triple loop (see symfun_warp.cu for the derivation) ---------------------------
+    double csum[GW][3], phi[GW];
+#pragma unroll
+    for (int e = 0; e < GW; e++) { csum[e][0] = csum[e][1] = csum[e][2] = 0.0; phi[e] = 0.0; }
+
+    double acc[GW][3];
+    auto sweep_step = [&](const double* sc) {
+      const double F = sc[1];
+      const double E = kb_exp_tab(-eta * sc[11], TAB);  // e^{-eta (rij^2 + rik^2 + rjk^2)}, :770
+      const double eF = E * F, Ee = E * eta;
+      const double v1x = eF * sc[2], v1y = eF * sc[3], v1z = eF * sc[4];
+      const double v2x = fma(Ee, sc[5], E * sc[8]), v2y = fma(Ee, sc[6], E * sc[9]),
+                   v2z = fma(Ee, sc[7], E * sc[10]);
+#pragma unroll
+      for (int e = 0; e < GW; e += 2)
+      {
+        const double2 c2 = *reinterpret_cast<const double2*>(sc + 12 + e);
+        const double2 d2 = *reinterpret_cast<const double2*>(sc + 20 + e);
+        phi[e] = fma(c2.x, eF, phi[e]);
+        phi[e + 1] = fma(c2.y, eF, phi[e + 1]);
+        if (GRAD)
+        {
+          acc[e][0] = fma(c2.x, v2x, fma(d2.x, v1x, acc[e][0]));
+          acc[e][1] = fma(c2.x, v2y, fma(d2.x, v1y, acc[e][1]));
+          acc[e][2] = fma(c2.x, v2z, fma(d2.x, v1z, acc[e][2]));
+          acc[e + 1][0] = fma(c2.y, v2x, fma(d2.y, v1x, acc[e + 1][0]));
+          acc[e + 1][1] = fma(c2.y, v2y, fma(d2.y, v1y, acc[e + 1][1]));
+          acc[e + 1][2] = fma(c2.y, v2z, fma(d2.y, v1z, acc[e + 1][2]));
+        }
+      }
+    };
+
+    const int nwi = (n + KPW - 1) / KPW;
+    for (int wi = 0; wi < nwi; wi++)
+    {
+      const int kk = wi * KPW + ksub;
+      const bool valid_k = kk < n;
+      const int k = valid_k ? KORD[kk] : 0;
+      const int degk = valid_k ? DEG[k] : 0;
+      const int maxdeg = __reduce_max_sync(FULL, degk);
+      double* scg = SC + ksub * (NGP * SCW + 2);  // this slot's scratch group
+
+#pragma unroll
+      for (int e = 0; e < GW; e++) acc[e][0] = acc[e][1] = acc[e][2] = 0.0;
+
+      for (int s0 = 0; s0 < maxdeg; s0 += NGP)
+      {
+        double* sc = scg + g * SCW;
+        if (s0 + g < degk)
+        {
+          const double* tk = TJ + k * SJ;
+          const double rik = tk[0], rik2 = tk[1], irik = tk[2], fik = tk[3], dfik = tk[4];
+          const double ukx = tk[5], uky = tk[6], ukz = tk[7];
+          const int j = JL[k * NP + s0 + g];
+          const int rcd = JR[k * NP + s0 + g];
+          const double* tj = TJ + j * SJ;
+          const double* rk = RK + rcd * SR;
+          const double rij2 = tj[1], irij = tj[2], fij = tj[3];
+          const double rjk = rk[0], irjk = rk[1], fjk = rk[2], dfjk = rk[3];
+          const double wx = (XYZ[k] - XYZ[j]) * irjk, wy = (XYZ[NP + k] - XYZ[NP + j]) * irjk,
+                       wz = (XYZ[2 * NP + k] - XYZ[2 * NP + j]) * irjk;      // unit vector j -> k
+          const double rjk2 = rjk * rjk;
+          const double h = 0.5 * irij * irik;
+          const double ct = (rij2 + rik2 - rjk2) * h;            // cos(theta_jik), :744
+          const double dct_ik = (rik2 - rij2 + rjk2) * h * irik;  // :746
+          const double dct_jk = -2.0 * rjk * h;                   // :747
+          const double fijk = fij * fjk;
+          const double F = fijk * fik;
+          const double dF_ik = dfik * fijk, dF_jk = dfjk * (fij * fik);
+          const double a = -2.0 * F * rik, b = -2.0 * F * rjk;
+          sc[1] = F;
+          sc[2] = dct_ik * ukx + dct_jk * wx; sc[3] = dct_ik * uky + dct_jk * wy; sc[4] = dct_ik * ukz + dct_jk * wz;
+          sc[5] = a * ukx + b * wx;           sc[6] = a * uky + b * wy;           sc[7] = a * ukz + b * wz;
+          sc[8] = dF_ik * ukx + dF_jk * wx;   sc[9] = dF_ik * uky + dF_jk * wy;   sc[10] = dF_ik * ukz + dF_jk * wz;
+          sc[11] = rij2 + rik2 + rjk2;
+#pragma unroll
+          for (int si2 = 0; si2 < 2; si2++)  // (1 +- cos)^{1,2,4,16} and derivative factors, :749-767
+          {
+            const double lam = si2 ? 1.0 : -1.0;
+            double bse = fma(lam, ct, 1.0);
+            const bool ok = bse > 0.0;  // guard of :755-767
+            bse = ok ? bse : 0.0;
+            const double b2 = bse * bse, b3 = b2 * bse, b4 = b2 * b2, b8 = b4 * b4;
+            const double b16 = b8 * b8, b15 = b8 * b4 * b3;
+            sc[12 + 0 + si2] = bse; sc[20 + 0 + si2] = ok ? lam : 0.0;
+            sc[12 + 2 + si2] = b2;  sc[20 + 2 + si2] = 2.0 * lam * bse;
+            sc[12 + 4 + si2] = b4;  sc[20 + 4 + si2] = 4.0 * lam * b3;
+            sc[12 + 6 + si2] = b16; sc[20 + 6 + si2] = 16.0 * lam * b15;
+          }
+        }
+        else
+        {
+#pragma unroll
+          for (int q = 1; q < 12; q++) sc[q] = 0.0;  // empty entry: contributes exactly zero
+        }
+        const int left = maxdeg - s0;
+        const int maxcnt = left < NGP ? left : NGP;  // warp-uniform
+        __syncwarp();
+
+        int ej = 0;
+#pragma unroll 1
+        for (; ej + 1 < maxcnt; ej += 2)
+        {
+          sweep_step(scg + ej * SCW);
+          sweep_step(scg + (ej + 1) * SCW);
+        }
+        if (ej < maxcnt) sweep_step(scg + ej * SCW);
+        __syncwarp();
+      }
+
+      if (GRAD && valid_k && valid_g)
+      {
+        // all row addresses first (distinct registers), then the stores back to back: with the
+        // address formed next to each store the compiler recycles one register pair and every
+        // store waits for the previous one to leave (ncu: long-scoreboard stalls on the address)
+        TOut* o[GW];
+#pragma unroll
+        for (int e = 0; e < GW; e++) o[e] = blk + (unsigned) ((gout[e] < 0 ? 0 : gout[e]) * row + 3 * k);
+#pragma unroll
+        for (int e = 0; e < GW; e++)
+        {
+          csum[e][0] += acc[e][0]; csum[e][1] += acc[e][1]; csum[e][2] += acc[e][2];
+          if (gout[e] >= 0)
+          {
+            o[e][0] = (TOut) (p2tab[e] * acc[e][0]); o[e][1] = (TOut) (p2tab[e] * acc[e][1]);
+            o[e][2] = (TOut) (p2tab[e] * acc[e][2]);
+          }
+        }
+      }
+    }
+
+    // ---- phase F: centre slot (translation invariance) and zeta, reduced over the slot lanes ----
+#pragma unroll
+    for (int e = 0; e < GW; e++)
+    {
+      for (int m = NGP; m < 32; m <<= 1)
+      {
+        phi[e] += shfl_xor_d(phi[e], m);
+        if (GRAD)
+        {
+          csum[e][0] += shfl_xor_d(csum[e][0], m);
+          csum[e][1] += shfl_xor_d(csum[e][1], m);
+          csum[e][2] += shfl_xor_d(csum[e][2], m);
+        }
+      }
+      if (ksub == 0 && gout[e] >= 0)
+      {
+        zrow[gout[e]] = 0.5 * p2tab[e] * phi[e];  // each unordered triple was visited twice
+        if (GRAD)
+        {
+          TOut* o = blk + (unsigned) (gout[e] * row + 3 * n);
+          o[0] = (TOut) (-p2tab[e] * csum[e][0]); o[1] = (TOut) (-p2tab[e] * csum[e][1]);
+          o[2] = (TOut) (-p2tab[e] * csum[e][2]);
+        }
+      }
+    }
+    if (GRAD)
+    {
+      const int len = (int) (A.dz_ptr[t + 1] - A.dz_ptr[t]);
+      for (int q = D * row + lane; q < len; q += 32) blk[q] = (TOut) 0;  // alignment padding
+    }
+  }
+}
+
+}  // namespace
+
+// Returns KB_OK and *launched = true when the parameter set is one these kernels handle.  Atoms
+// with more than 64 neighbors (or more pair records than fit) are appended to d_overflow and left
+// to the caller's second pass.
+int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
+                           const int32_t* d_subset, const double* d_coords, const int32_t* d_species,
+                           const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn, double* d_zeta,
+                           void* d_dz, int dz_dtype, const int64_t* d_dz_ptr, int32_t* d_overflow,
+                           bool* launched, bool* may_overflow, cudaStream_t st)
+{
+  *launched = false;
+  *may_overflow = false;
+  if (n_centers <= 0) return KB_OK;
+  if (!P.canonical_zl || P.n_groups < 1) return KB_OK;
+  for (int g = 0; g < P.n_groups; g++)
+    if (P.grp_kind[g] != KB_G4) return KB_OK;
+  int NGP = 1;
+  while (NGP < P.n_groups) NGP <<= 1;
+  if (NGP > 32) return KB_OK;
+  int NP = maxn < 2 ? 2 : maxn;
+  if (NP > 64) { NP = 64; *may_overflow = true; }
+  NP = (NP + 1) & ~1;
+  const int worst = NP * (NP - 1) / 2;
+  const bool grad = d_dz != nullptr;
+  const size_t limit = 227 * 1024, per_block_reserve = 1024;
+  const size_t extra = (size_t) SC_DOUBLES * 8 + 64 * 8;
+  // record capacity: worst case when that still leaves the wanted residency, else what fits (never
+  // below 45 % of the worst case: a filled sphere has ~44 % of its neighbor pairs within the cutoff)
+  const int want = grad ? KB_SWEEP_MIN_BLOCKS : KB_SWEEP_MIN_BLOCKS_NOGRAD;
+  int RC = worst;
+  {
+    const size_t budget = limit / want - per_block_reserve;
+    const size_t fixed = rec_layout(NP, 0).bytes + extra;
+    if (fixed + 32 * (size_t) RC > budget)
+    {
+      const int floor_rc = (worst * 9 + 19) / 20;
+      long long cap = budget > fixed ? (long long) ((budget - fixed) / 32) : 0;
+      RC = cap > floor_rc ? (int) cap : floor_rc;
+      if (RC > worst) RC = worst;
+    }
+  }
+  while (RC > 8 && rec_layout(NP, RC).bytes + extra > limit) RC = RC * 3 / 4;
+  if (RC < worst) *may_overflow = true;
+  const RecLayout L = rec_layout(NP, RC);
+  const size_t sweep_smem = L.bytes + extra;
+  if (sweep_smem > limit) return KB_OK;
+  const size_t prep_warp = prep_smem_bytes(P, NP, RC);
+  if (prep_warp * PREP_WARPS > limit) return KB_OK;
+
+  int dev = 0, sms = 148;
+  KB_CUDA(cudaGetDevice(&dev));
+  KB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  // chunk of atoms whose records are alive at the same time
+  int chunk = 1 << 18;
+  if (const char* c = getenv("KB_SPLIT_CHUNK")) { const int v = atoi(c); if (v >= 1024) chunk = v; }
+  if (chunk > n_centers) chunk = n_centers;
+  const int n_chunks = (n_centers + chunk - 1) / chunk;
+  unsigned char* records = nullptr;
+  int32_t* work = nullptr;
+  KB_CUDA(cudaMallocAsync((void**) &records, (size_t) chunk * L.bytes, st));
+  KB_CUDA(cudaMallocAsync((void**) &work, sizeof(int32_t) * (size_t) n_chunks, st));
+  KB_CUDA(cudaMemsetAsync(work, 0, sizeof(int32_t) * (size_t) n_chunks, st));
+
+  SplitArgs A;
+  A.centers = d_centers; A.subset = d_subset; A.coords = d_coords; A.species = d_species;
+  A.nl_off = d_nl_off; A.nl_idx = d_nl_idx; A.zeta = d_zeta; A.dz = d_dz; A.dz_ptr = d_dz_ptr;
+  A.overflow = d_overflow; A.records = records; A.NP = NP; A.RC = RC; A.NGP = NGP;
+
+  int per_sm = (int) (limit / (sweep_smem + per_block_reserve));
+  if (per_sm > want) per_sm = want;
+  if (const char* cap = getenv("KB_WARPS_PER_SM"))  // tuning experiments only
+  {
+    const int c = atoi(cap);
+    if (c >= 1 && c < per_sm) per_sm = c;
+  }
+  if (per_sm < 1) per_sm = 1;
+
+  int rc = KB_OK;
+#define KB_SPLIT_LAUNCH(G, T)                                                                          \
+  do {                                                                                                 \
+    cudaError_t e_ = cudaFuncSetAttribute(symfun_prep_kernel<G, T>,                                    \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+                                          (int) (prep_warp * PREP_WARPS));                             \
+    if (e_ == cudaSuccess)                                                                             \
+      e_ = cudaFuncSetAttribute(symfun_sweep_kernel<G, T>,                                             \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem);        \
+    if (e_ != cudaSuccess) { rc = -(int) e_; break; }                                                  \
+    symfun_prep_kernel<G, T><<<pgrid, PREP_WARPS * 32, prep_warp * PREP_WARPS, st>>>(P, A,             \
+                                                                                     (int) prep_warp); \
+    symfun_sweep_kernel<G, T><<<sgrid, 32, sweep_smem, st>>>(P, A);                                    \
+  } while (0)
+  for (int c = 0; c < n_chunks && rc == KB_OK; c++)
+  {
+    A.lo = c * chunk;
+    A.hi = A.lo + chunk < n_centers ? A.lo + chunk : n_centers;
+    A.work = work + c;
+    const int cnt = A.hi - A.lo;
+    int pgrid = (cnt + PREP_WARPS - 1) / PREP_WARPS;
+    if (pgrid > sms * 16) pgrid = sms * 16;
+    int sgrid = sms * per_sm;
+    if (sgrid > cnt) sgrid = cnt;
+    if (!grad) KB_SPLIT_LAUNCH(false, double);
+    else if (dz_dtype == KB_F32) KB_SPLIT_LAUNCH(true, float);
+    else KB_SPLIT_LAUNCH(true, double);
+    if (rc == KB_OK)
+    {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) rc = -(int) e;
+      else kb_note_launch(2);
+    }
+  }
+#undef KB_SPLIT_LAUNCH
+  cudaFreeAsync(records, st);
+  cudaFreeAsync(work, st);
+  if (rc == KB_OK) *launched = true;
+  return rc;
+}

@@ -1,5 +1,6 @@
 """First-light timing of the hot path on one B200 (not the bench contract; see bench.py)."""
 import json
+import os
 import sys
 import time
 
@@ -40,6 +41,7 @@ def main():
     print("fp64 peak TFLOP/s", ops.probe_fp64_peak())
     print("hbm copy GB/s", ops.probe_hbm_copy(1 << 30))
     P = ops.build_params(get_set51(), np.array([[5.0]]))
+    mode = int(os.environ.get("KB_MODE", "0"))  # include/kliff_b200.h KB_SYMFUN_*
     for nx in [int(a) for a in sys.argv[1:]] or [10, 30, 50]:
         cell, pos = diamond(nx)
         n = len(pos)
@@ -52,9 +54,9 @@ def main():
         dz_ptr, total = ops.block_offsets(n, None, offsets, 51)
         dz = torch.empty(total, dtype=torch.float64, device=dev)
         t_sf, (zeta, _, _) = timed(lambda: ops.symfun_forward(P, allc, species, offsets, indices, maxn,
-                                                              n_centers=n, dz_ptr=dz_ptr, dz=dz))
+                                                              n_centers=n, dz_ptr=dz_ptr, dz=dz, mode=mode))
         t_z, _ = timed(lambda: ops.symfun_forward(P, allc, species, offsets, indices, maxn,
-                                                  n_centers=n, grad=False))
+                                                  n_centers=n, grad=False, mode=mode))
         image = torch.cat([torch.arange(n, dtype=torch.int32, device=dev), pi])
         pack = dict(offsets=offsets, indices=indices, image=image, dz=dz, dz_ptr=dz_ptr, D=51, n_out=n)
         w = torch.randn(n, 51, dtype=torch.float64, device=dev)
