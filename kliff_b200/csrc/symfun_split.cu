@@ -84,12 +84,94 @@ struct SplitArgs
 
 __host__ __device__ inline size_t prep_smem_bytes(const kb_symfun_params& P, int NP, int RC)
 {
-  size_t b = (size_t) 24 * NP + 32 * (size_t) P.n_two + 8 * (size_t) P.n_species * P.n_species;
+  size_t b = (size_t) 24 * NP + 32 * (size_t) P.n_two + 24 * (size_t) P.n_species * P.n_species;
   b += (size_t) 8 * NP + 4 * NP + 4 * NP;           // ADJ, SPC, BASE
   b = (b + 15) & ~(size_t) 15;
   b += al16(2 * NP * NP) + al16(NP * NP);           // JR, JL (copied out as 16-byte words)
   b += (size_t) 2 * RC + 2 * (size_t) NP;           // PAIR, DEG + KORD
   return (b + 15) & ~(size_t) 15;
+}
+
+// ---- adjacency among the neighbors of one atom ------------------------------------------------
+__device__ __forceinline__ int popc_m(unsigned m) { return __popc(m); }
+__device__ __forceinline__ int popc_m(unsigned long long m) { return __popcll(m); }
+__device__ __forceinline__ int ffs_m(unsigned m) { return __ffs((int) m); }
+__device__ __forceinline__ int ffs_m(unsigned long long m) { return __ffsll((long long) m); }
+
+// Lane = row j computes its adjacency row in registers with the reference predicate
+// !(sqrt(r2) > rc) (sym_fn.cpp:729), decided on r2 against pre-squared thresholds whenever that
+// is unambiguous; a warp scan numbers the (j < k) pairs ("records"); then every slot gets its
+// ascending neighbor list JL with the record id JR of each entry, and PAIR lists the records.
+// Returns the number of records (nothing is written beyond RC).
+template <typename M>
+__device__ __forceinline__ int build_lists(int n, int NP, int S, M act, const double* XYZ, const int* SPC,
+                                           const double* rcut, const double* R2LO, const double* R2HI,
+                                           M* ADJ, int* BASE, unsigned char* DEG, unsigned char* JL,
+                                           unsigned short* JR, unsigned short* PAIR, int RC, int lane)
+{
+  const unsigned FULL = 0xffffffffu;
+  const M one = 1;
+  int nrec = 0;
+  for (int j0 = 0; j0 < n; j0 += 32)
+  {
+    const int j = j0 + lane;
+    M mask = 0;
+    if (j < n)
+    {
+      const double xj = XYZ[j], yj = XYZ[NP + j], zj = XYZ[2 * NP + j];
+      const int prow = SPC[j] * S;
+      for (int k = 0; k < n; k++)
+      {
+        const double r2 = xnorm2(xsub(XYZ[k], xj), xsub(XYZ[NP + k], yj), xsub(XYZ[2 * NP + k], zj));
+        const int pr = prow + SPC[k];
+        bool hit = r2 < R2LO[pr];
+        if (!hit && r2 <= R2HI[pr]) hit = !(sqrt(r2) > rcut[pr]);
+        mask |= (M) hit << k;
+      }
+      mask &= ~(one << j) & act;
+      if (!((act >> j) & one)) mask = 0;
+    }
+    const int upper = (j + 1 < (int) (8 * sizeof(M))) ? popc_m((M) (mask >> (j + 1))) : 0;
+    int inc = upper;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const int y = __shfl_up_sync(FULL, inc, d);
+      if (lane >= d) inc += y;
+    }
+    if (j < n)
+    {
+      ADJ[j] = mask;
+      DEG[j] = (unsigned char) popc_m(mask);
+      BASE[j] = nrec + inc - upper;
+    }
+    nrec += __shfl_sync(FULL, inc, 31);
+  }
+  __syncwarp();
+  if (nrec > RC) return nrec;
+  for (int k = lane; k < n; k += 32)
+  {
+    M m = ADJ[k];
+    int idx = 0;
+    int up = BASE[k];  // records of pairs (k, j > k) are numbered consecutively from BASE[k]
+    while (m)
+    {
+      const int j = ffs_m(m) - 1;
+      m &= m - one;
+      int slot;
+      if (j > k) { slot = up++; PAIR[slot] = (unsigned short) (k | (j << 8)); }
+      else
+      {
+        const M between = (M) (ADJ[j] >> (j + 1)) & ((one << (k - j - 1)) - one);
+        slot = BASE[j] + popc_m(between);
+      }
+      JL[k * NP + idx] = (unsigned char) j;
+      JR[k * NP + idx] = (unsigned short) slot;
+      idx++;
+    }
+  }
+  __syncwarp();
+  return nrec;
 }
 
 // =============================================================================================
@@ -109,7 +191,9 @@ symfun_prep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A
   double* XYZ = reinterpret_cast<double*>(base);      // [3][NP]
   double* Z2 = XYZ + 3 * NP;                          // [NT] radial zeta, [3 NT] radial centre slot
   double* RCI = Z2 + 4 * NT;                          // [S][S] 1 / rc
-  unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(RCI + S * S);  // [NP]
+  double* R2LO = RCI + S * S;                         // [S][S] rc^2 (1 - 1e-12): surely inside
+  double* R2HI = R2LO + S * S;                        // [S][S] rc^2 (1 + 1e-12): surely outside beyond
+  unsigned long long* ADJ = reinterpret_cast<unsigned long long*>(R2HI + S * S);  // [NP]
   int* SPC = reinterpret_cast<int*>(ADJ + NP);        // [NP]
   int* BASE = SPC + NP;                               // [NP]
   unsigned char* p = reinterpret_cast<unsigned char*>(BASE + NP);
@@ -120,7 +204,13 @@ symfun_prep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A
   unsigned char* DEG = reinterpret_cast<unsigned char*>(PAIR + RC);  // [NP]
   unsigned char* KORD = DEG + NP;                                     // [NP]
 
-  for (int q = lane; q < S * S; q += 32) RCI[q] = 1.0 / P.rcut[q];
+  for (int q = lane; q < S * S; q += 32)
+  {
+    const double rc = P.rcut[q], rc2 = rc * rc;
+    RCI[q] = 1.0 / rc;
+    R2LO[q] = rc2 * (1.0 - 1e-12);
+    R2HI[q] = rc2 * (1.0 + 1e-12);
+  }
   __syncwarp();
 
   const int stride = gridDim.x * PREP_WARPS;
@@ -216,66 +306,17 @@ symfun_prep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A
       }
     }
 
-    // ---- phase B: adjacency rows (reference predicate r_jk <= rc_jk, sym_fn.cpp:729) ------------
-    int nrec = 0;
-    for (int j0 = 0; j0 < n; j0 += 32)
-    {
-      const int j = j0 + lane;
-      unsigned long long mask = 0ull;
-      if (j < n && ((ACT >> j) & 1ull))
-      {
-        const double xj = XYZ[j], yj = XYZ[NP + j], zj = XYZ[2 * NP + j];
-        const double* rcrow = P.rcut + SPC[j] * S;
-        for (int k = 0; k < n; k++)
-        {
-          const double r2 = xnorm2(xsub(XYZ[k], xj), xsub(XYZ[NP + k], yj), xsub(XYZ[2 * NP + k], zj));
-          const double rc = rcrow[SPC[k]];
-          const double rc2 = rc * rc;
-          bool hit = r2 < rc2 * (1.0 - 1e-12);
-          if (!hit && r2 <= rc2 * (1.0 + 1e-12)) hit = !(sqrt(r2) > rc);
-          if (hit && k != j && ((ACT >> k) & 1ull)) mask |= 1ull << k;
-        }
-      }
-      const int upper = (j < 63) ? __popcll(mask >> (j + 1)) : 0;
-      int inc = upper;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1)
-      {
-        const int y = __shfl_up_sync(FULL, inc, d);
-        if (lane >= d) inc += y;
-      }
-      if (j < n)
-      {
-        ADJ[j] = mask;
-        DEG[j] = (unsigned char) __popcll(mask);
-        BASE[j] = nrec + inc - upper;
-      }
-      nrec += __shfl_sync(FULL, inc, 31);
-    }
+    // ---- phase B: adjacency rows + per-slot lists (32-bit masks when every list fits in 32) ----
+    const int nrec = NP <= 32
+        ? build_lists<unsigned>(n, NP, S, (unsigned) ACT, XYZ, SPC, P.rcut, R2LO, R2HI,
+                                reinterpret_cast<unsigned*>(ADJ), BASE, DEG, JL, JR, PAIR, RC, lane)
+        : build_lists<unsigned long long>(n, NP, S, ACT, XYZ, SPC, P.rcut, R2LO, R2HI, ADJ, BASE, DEG, JL,
+                                          JR, PAIR, RC, lane);
     if (nrec > RC)
     {
       if (lane == 0) { A.overflow[2 + atomicAdd(A.overflow, 1)] = t; hdr[0] = -1; hdr[1] = 0; }
       continue;
     }
-    __syncwarp();
-    for (int k = lane; k < n; k += 32)
-    {
-      unsigned long long m = ADJ[k];
-      int idx = 0;
-      while (m)
-      {
-        const int j = __ffsll((long long) m) - 1;
-        m &= m - 1ull;
-        const int a = j < k ? j : k, b = j < k ? k : j;
-        const unsigned long long between = (ADJ[a] >> (a + 1)) & ((1ull << (b - a - 1)) - 1ull);
-        const int slot = BASE[a] + __popcll(between);
-        JL[k * NP + idx] = (unsigned char) j;
-        JR[k * NP + idx] = (unsigned short) slot;
-        if (j > k) PAIR[slot] = (unsigned short) (k | (j << 8));
-        idx++;
-      }
-    }
-    __syncwarp();
 
     // ---- phase C: pair-jk records; lanes = records, two per trip ---------------------------------
     for (int r0 = lane; r0 < nrec; r0 += 64)
@@ -526,7 +567,12 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
         // store waits for the previous one to leave (ncu: long-scoreboard stalls on the address)
         TOut* o[GW];
 #pragma unroll
-        for (int e = 0; e < GW; e++) o[e] = blk + (unsigned) ((gout[e] < 0 ? 0 : gout[e]) * row + 3 * k);
+        for (int e = 0; e < GW; e++)
+        {
+          o[e] = blk + (unsigned) ((gout[e] < 0 ? 0 : gout[e]) * row + 3 * k);
+          asm volatile("" : "+l"(o[e]));  // keep the eight addresses in eight register pairs
+          __builtin_assume(__isGlobal(o[e]));
+        }
 #pragma unroll
         for (int e = 0; e < GW; e++)
         {
@@ -543,7 +589,6 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
     // ---- phase F: centre slot (translation invariance) and zeta, reduced over the slot lanes ----
 #pragma unroll
     for (int e = 0; e < GW; e++)
-    {
       for (int m = NGP; m < 32; m <<= 1)
       {
         phi[e] += shfl_xor_d(phi[e], m);
@@ -554,16 +599,31 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
           csum[e][2] += shfl_xor_d(csum[e][2], m);
         }
       }
-      if (ksub == 0 && gout[e] >= 0)
+    if (ksub == 0)
+    {
+      TOut* o[GW];
+      double* z[GW];
+#pragma unroll
+      for (int e = 0; e < GW; e++)
       {
-        zrow[gout[e]] = 0.5 * p2tab[e] * phi[e];  // each unordered triple was visited twice
-        if (GRAD)
-        {
-          TOut* o = blk + (unsigned) (gout[e] * row + 3 * n);
-          o[0] = (TOut) (-p2tab[e] * csum[e][0]); o[1] = (TOut) (-p2tab[e] * csum[e][1]);
-          o[2] = (TOut) (-p2tab[e] * csum[e][2]);
-        }
+        const int d = gout[e] < 0 ? 0 : gout[e];
+        z[e] = zrow + d;
+        o[e] = GRAD ? blk + (unsigned) (d * row + 3 * n) : nullptr;
+        asm volatile("" : "+l"(o[e]), "+l"(z[e]));  // distinct address registers: stores back to back
+        __builtin_assume(__isGlobal(o[e]));
+        __builtin_assume(__isGlobal(z[e]));
       }
+#pragma unroll
+      for (int e = 0; e < GW; e++)
+        if (gout[e] >= 0)
+        {
+          *z[e] = 0.5 * p2tab[e] * phi[e];  // each unordered triple was visited twice
+          if (GRAD)
+          {
+            o[e][0] = (TOut) (-p2tab[e] * csum[e][0]); o[e][1] = (TOut) (-p2tab[e] * csum[e][1]);
+            o[e][2] = (TOut) (-p2tab[e] * csum[e][2]);
+          }
+        }
     }
     if (GRAD)
     {
