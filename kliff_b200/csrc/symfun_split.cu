@@ -28,17 +28,26 @@
 namespace {
 
 constexpr int GW = KB_GROUP_WIDTH;
-constexpr int SCW = 28;  // doubles per scratch entry: 12 geometry + 8 C + 8 C'
+// doubles per scratch entry: 12 geometry + 8 C + 8 C' + 2 of padding, so that the eight lanes of a slot
+// (which write eight consecutive entries at once) start on eight different 16-byte bank groups:
+// 60 words = 28 mod 32 -> lane g starts at bank 28 g mod 32 = 0,28,24,...,4 (28 doubles gave a 2-way conflict)
+constexpr int SCW = 30;
 constexpr int SC_DOUBLES = 32 * SCW + 2 * 32;
 constexpr int SJ = 8, SR = 4;
 constexpr int PREP_WARPS = 4;
 
-#ifndef KB_SWEEP_MIN_BLOCKS
-#define KB_SWEEP_MIN_BLOCKS 8
+// Register caps of the sweep kernel (one warp per CTA) and the resident warps per SM they allow.
+// The gradient variant wants ~248 registers (8 warps per SM).  Capping it lower buys residency
+// (200 -> 10 warps with 5 doubles spilled) but measures slower (7.7 -> 8.2 ms on 216k atoms): the
+// kernel is bound by the shared-memory data pipe and the FP64 pipe, not by latency.
+#ifndef KB_SWEEP_REGS
+#define KB_SWEEP_REGS 248
 #endif
-#ifndef KB_SWEEP_MIN_BLOCKS_NOGRAD
-#define KB_SWEEP_MIN_BLOCKS_NOGRAD 12
+#ifndef KB_SWEEP_REGS_NOGRAD
+#define KB_SWEEP_REGS_NOGRAD 128
 #endif
+#define KB_SWEEP_MIN_BLOCKS (65536 / (32 * KB_SWEEP_REGS))
+#define KB_SWEEP_MIN_BLOCKS_NOGRAD (65536 / (32 * KB_SWEEP_REGS_NOGRAD))
 #ifndef KB_PREP_MIN_BLOCKS
 #define KB_PREP_MIN_BLOCKS 6  // 80 registers: 24 resident warps per SM, no spills
 #endif
@@ -373,7 +382,7 @@ symfun_prep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A
 // stage 2: triple sweep
 // =============================================================================================
 template <bool GRAD, typename TOut>
-__global__ void __launch_bounds__(32, GRAD ? KB_SWEEP_MIN_BLOCKS : KB_SWEEP_MIN_BLOCKS_NOGRAD)
+__global__ void __maxnreg__(GRAD ? KB_SWEEP_REGS : KB_SWEEP_REGS_NOGRAD)
 symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -457,8 +466,9 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
 
     double acc[GW][3];
     auto sweep_step = [&](const double* sc) {
-      const double F = sc[1];
-      const double E = kb_exp_tab(-eta * sc[11], TAB);  // e^{-eta (rij^2 + rik^2 + rjk^2)}, :770
+      const double2 sF = *reinterpret_cast<const double2*>(sc);  // {rij^2 + rik^2 + rjk^2, F}
+      const double F = sF.y;
+      const double E = kb_exp_tab(-eta * sF.x, TAB);  // e^{-eta (rij^2 + rik^2 + rjk^2)}, :770
       const double eF = E * F, Ee = E * eta;
       const double v1x = eF * sc[2], v1y = eF * sc[3], v1z = eF * sc[4];
       const double v2x = fma(Ee, sc[5], E * sc[8]), v2y = fma(Ee, sc[6], E * sc[9]),
@@ -520,11 +530,11 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
           const double F = fijk * fik;
           const double dF_ik = dfik * fijk, dF_jk = dfjk * (fij * fik);
           const double a = -2.0 * F * rik, b = -2.0 * F * rjk;
+          sc[0] = rij2 + rik2 + rjk2;
           sc[1] = F;
           sc[2] = dct_ik * ukx + dct_jk * wx; sc[3] = dct_ik * uky + dct_jk * wy; sc[4] = dct_ik * ukz + dct_jk * wz;
           sc[5] = a * ukx + b * wx;           sc[6] = a * uky + b * wy;           sc[7] = a * ukz + b * wz;
           sc[8] = dF_ik * ukx + dF_jk * wx;   sc[9] = dF_ik * uky + dF_jk * wy;   sc[10] = dF_ik * ukz + dF_jk * wz;
-          sc[11] = rij2 + rik2 + rjk2;
 #pragma unroll
           for (int si2 = 0; si2 < 2; si2++)  // (1 +- cos)^{1,2,4,16} and derivative factors, :749-767
           {
@@ -543,7 +553,7 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
         else
         {
 #pragma unroll
-          for (int q = 1; q < 12; q++) sc[q] = 0.0;  // empty entry: contributes exactly zero
+          for (int q = 0; q < 11; q++) sc[q] = 0.0;  // empty entry: contributes exactly zero
         }
         const int left = maxdeg - s0;
         const int maxcnt = left < NGP ? left : NGP;  // warp-uniform
