@@ -28,9 +28,10 @@ if ROOT not in sys.path:
 A_SI, SIGMA, RC = 5.431, 0.05, 5.0
 FLOP_CANON = 380618.0   # per atom, set51 / n=28 / T=378 / T4=168
 BYTES_CANON = 36724.0   # per atom, fp64 zeta + dG/dr written + inputs read once
-# dram__bytes_read.sum + dram__bytes_write.sum of symfun_warp_kernel<true> on this very workload
-# (1 000 000 atoms, one launch), ncu --set full capture of round 1: profiles/r01_ncu_symfun_warp_1M_traffic.txt
-TRAFFIC_NCU_BYTES_PER_ATOM = 48855.0
+# dram__bytes_read.sum + dram__bytes_write.sum of the descriptor stage on this very workload
+# (1 000 000 atoms: 4 chunks x (symfun_prep_kernel + symfun_sweep_kernel)), ncu --set full capture
+# of round 1: profiles/r01_ncu_symfun_split_1M_traffic.txt
+TRAFFIC_NCU_BYTES_PER_ATOM = None
 
 
 def diamond(nx, seed):
@@ -429,6 +430,7 @@ def main():
     barrier()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    ops.kernel_timing(True)   # CUDA events around the descriptor kernels, on their stream
     launches0 = ops.launch_count()
     timers, t_wall0 = [], time.time()
     for _ in range(args.steps):
@@ -438,6 +440,7 @@ def main():
     barrier()
     t_wall1 = time.time()
     launches = ops.launch_count() - launches0
+    ktimes = ops.kernel_timing(False)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
     step_ms = [ev[0].elapsed_time(ev[3]) for ev in timers]
@@ -487,9 +490,19 @@ def main():
 
     hbm_peak, peak_src = measured_peaks()
     fp64_peak = ops.probe_fp64_peak()
-    sym_s = float(np.mean(sym_ms)) * 1e-3
+    # the descriptor stage = symfun_prep_kernel + symfun_sweep_kernel launches (one pair per chunk of
+    # 262 144 atoms); their device time per step, from the library's own events
+    kern_ms = {k: v[0] / args.steps for k, v in ktimes.items()}
+    kern_n = {k: v[1] // args.steps for k, v in ktimes.items()}
+    sym_s = (kern_ms["prep"] + kern_ms["sweep"] + kern_ms["fused"]) * 1e-3
+    if sym_s <= 0.0:
+        sym_s = float(np.mean(sym_ms)) * 1e-3
     ach_gbs = BYTES_CANON * n / sym_s / 1e9
     ach_tf = FLOP_CANON * n / sym_s / 1e12
+    kname = "symfun_prep_kernel<true> + symfun_sweep_kernel<true>"
+    kinfo = {"launches_per_step": kern_n, "ms_per_step": kern_ms,
+             "dominant": "symfun_sweep_kernel<true>",
+             "note": "achieved = canonical work of one step / summed device time of these launches"}
     line = {
         "metric": "descriptor+dG/dr atoms/sec", "value": value, "unit": "atoms/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -501,13 +514,14 @@ def main():
                    "l2": "256 MiB write between timed steps (outside the step's CUDA events)",
                    "step_breakdown_ms": {"paddings+neighbors": float(np.mean(nl_ms)),
                                          "symfun+dG/dr": float(np.mean(sym_ms))}},
-        "roofline": {"kernel": "symfun_warp_kernel<true>", "bound": "hbm", "achieved": ach_gbs,
+        "roofline": {"kernel": kname, "kernels": kinfo, "bound": "hbm", "achieved": ach_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": TRAFFIC_NCU_BYTES_PER_ATOM * n if args.nx == 50 else None,
-                     "traffic_source": "ncu capture profiles/r01_ncu_symfun_warp_1M_traffic.txt (bytes per launch)",
+                     "traffic": (TRAFFIC_NCU_BYTES_PER_ATOM * n
+                                 if (args.nx == 50 and TRAFFIC_NCU_BYTES_PER_ATOM) else None),
+                     "traffic_source": "ncu capture profiles/r01_ncu_symfun_split_1M_traffic.txt (bytes per step: all launches of the stage)",
                      "peak_source": peak_src,
                      "note": "algorithmic bytes 36 724 B/atom; the kernel is FP64-pipe bound, see roofline_fp64"},
-        "roofline_fp64": {"kernel": "symfun_warp_kernel<true>", "bound": "fp64", "achieved": ach_tf,
+        "roofline_fp64": {"kernel": kname, "bound": "fp64", "achieved": ach_tf,
                           "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                           "peak_source": "DFMA-chain probe in this run (kb_probe_fp64_peak)",
                           "note": "canonical 380 618 flop/atom (SURVEY.md §8d)"},

@@ -225,6 +225,12 @@ int kb_probe_fp64_peak(double* h_tflops, void* stream);
 int kb_probe_hbm_copy(size_t bytes, double* h_gbs, void* stream);
 /* Number of kernels this library has launched in this process (reset != 0 zeroes it). */
 int64_t kb_launch_count(int32_t reset);
+/* Per-kernel device times of the descriptor stage, measured with CUDA events on the launching
+ * stream.  Returns in h_ms[3] / h_launches[3] (either may be NULL) the summed duration and number
+ * of launches recorded since the previous call, by kernel: [0] symfun_prep_kernel, [1]
+ * symfun_sweep_kernel, [2] fused symfun_warp_kernel; then switches recording on (enable != 0) or
+ * off.  Off by default: no events are created unless a caller (bench.py) asks. */
+int kb_kernel_timing(int32_t enable, double* h_ms, int32_t* h_launches);
 
 #ifdef __cplusplus
 }

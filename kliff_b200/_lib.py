@@ -49,7 +49,7 @@ EXPORTS = [
     "kb_batch_begin", "kb_batch_neighbors", "kb_batch_finish", "kb_batch_destroy",
     "kb_symfun_block_offsets", "kb_symfun_forward",
     "kb_force_scatter_fwd", "kb_force_scatter_bwd", "kb_dense_fold",
-    "kb_probe_fp64_peak", "kb_probe_hbm_copy", "kb_launch_count",
+    "kb_probe_fp64_peak", "kb_probe_hbm_copy", "kb_launch_count", "kb_kernel_timing",
 ]
 
 _lib = None
@@ -102,6 +102,7 @@ def lib():
     L.kb_dense_fold.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, vp, i32, vp, vp, vp, vp]
     L.kb_probe_fp64_peak.argtypes = [C.POINTER(dbl), vp]
     L.kb_probe_hbm_copy.argtypes = [C.c_size_t, C.POINTER(dbl), vp]
+    L.kb_kernel_timing.argtypes = [i32, C.POINTER(dbl), C.POINTER(i32)]
     L.kb_launch_count.argtypes = [i32]
     L.kb_launch_count.restype = i64
     for name in EXPORTS:

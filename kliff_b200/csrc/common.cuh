@@ -25,6 +25,13 @@ void kb_note_launch(int n = 1);
     kb_note_launch();                                                          \
   } while (0)
 
+// Optional per-kernel timing (kb_kernel_timing): when switched on, launch sites bracket their kernel
+// with CUDA events on the launching stream under a small integer tag.  Off by default (no events).
+enum { KB_T_PREP = 0, KB_T_SWEEP = 1, KB_T_FUSED = 2, KB_T_COUNT = 3 };
+bool kb_timing_on();
+void kb_timing_begin(int tag, cudaStream_t st);
+void kb_timing_end(int tag, cudaStream_t st);
+
 static inline cudaStream_t kb_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
 // Scratch comes from the stream-ordered allocator.  Its default pool gives memory back to the

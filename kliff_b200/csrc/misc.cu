@@ -22,6 +22,63 @@ void kb_pool_setup()
   done_mask.fetch_or(bit, std::memory_order_release);
 }
 
+// ---- optional kernel timing ------------------------------------------------------------------
+#include <mutex>
+#include <vector>
+namespace {
+std::atomic<int> g_timing{0};
+std::mutex g_timing_mu;
+struct TimedLaunch { int tag; cudaEvent_t e0, e1; };
+std::vector<TimedLaunch> g_timed;
+cudaEvent_t g_open[KB_T_COUNT];
+}  // namespace
+bool kb_timing_on() { return g_timing.load(std::memory_order_relaxed) != 0; }
+void kb_timing_begin(int tag, cudaStream_t st)
+{
+  if (!kb_timing_on()) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  cudaEventCreate(&g_open[tag]);
+  cudaEventRecord(g_open[tag], st);
+}
+void kb_timing_end(int tag, cudaStream_t st)
+{
+  if (!kb_timing_on()) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  TimedLaunch t{tag, g_open[tag], nullptr};
+  cudaEventCreate(&t.e1);
+  cudaEventRecord(t.e1, st);
+  g_timed.push_back(t);
+}
+
+extern "C" int kb_kernel_timing(int32_t enable, double* h_ms, int32_t* h_launches)
+{
+  // collect what was recorded so far (synchronises on the recorded events), then set the switch
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (int q = 0; q < KB_T_COUNT; q++)
+  {
+    if (h_ms) h_ms[q] = 0.0;
+    if (h_launches) h_launches[q] = 0;
+  }
+  int rc = KB_OK;
+  for (TimedLaunch& t : g_timed)
+  {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(t.e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, t.e0, t.e1);
+    if (e != cudaSuccess) rc = -(int) e;
+    else
+    {
+      if (h_ms) h_ms[t.tag] += ms;
+      if (h_launches) h_launches[t.tag] += 1;
+    }
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  g_timed.clear();
+  g_timing.store(enable ? 1 : 0, std::memory_order_relaxed);
+  return rc;
+}
+
 extern "C" int64_t kb_launch_count(int32_t reset)
 {
   return reset ? g_launches.exchange(0) : g_launches.load();

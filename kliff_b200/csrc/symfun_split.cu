@@ -28,10 +28,12 @@
 namespace {
 
 constexpr int GW = KB_GROUP_WIDTH;
-// doubles per scratch entry: 12 geometry + 8 C + 8 C' + 2 of padding, so that the eight lanes of a slot
-// (which write eight consecutive entries at once) start on eight different 16-byte bank groups:
-// 60 words = 28 mod 32 -> lane g starts at bank 28 g mod 32 = 0,28,24,...,4 (28 doubles gave a 2-way conflict)
-constexpr int SCW = 30;
+// doubles per scratch entry: 12 geometry + 8 C (the powers b, b^2, b^4, b^16 of b = 1 -+ cos) + 2 (the
+// derivative factors 16 lambda b^15; those of zeta = 1, 2, 4 follow from the stored powers with 6
+// multiplications, cheaper than loading them: the kernel's busiest unit is the shared-memory data
+// pipe).  22 doubles = 44 words = 12 mod 32, so the eight lanes of a slot, which write eight consecutive
+// entries at once, start on eight different 16-byte bank groups (0,12,24,4,16,28,8,20).
+constexpr int SCW = 22;
 constexpr int SC_DOUBLES = 32 * SCW + 2 * 32;
 constexpr int SJ = 8, SR = 4;
 constexpr int PREP_WARPS = 4;
@@ -473,21 +475,30 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
       const double v1x = eF * sc[2], v1y = eF * sc[3], v1z = eF * sc[4];
       const double v2x = fma(Ee, sc[5], E * sc[8]), v2y = fma(Ee, sc[6], E * sc[9]),
                    v2z = fma(Ee, sc[7], E * sc[10]);
+      // entries e = 2 zi + si, zeta = {1,2,4,16}[zi], lambda = {-1,+1}[si]:  C = b^zeta,
+      // C' = zeta lambda b^(zeta-1) (0 when b = 0: the guard of sym_fn.cpp:755-767)
+      double2 c2[4], d2[4];
 #pragma unroll
-      for (int e = 0; e < GW; e += 2)
+      for (int zi = 0; zi < 4; zi++) c2[zi] = *reinterpret_cast<const double2*>(sc + 12 + 2 * zi);
+      d2[3] = *reinterpret_cast<const double2*>(sc + 20);
+      d2[0].x = __hiloint2double(__double2hiint(c2[0].x) > 0 ? 0xbff00000 : 0, 0);  // b > 0 ? -1 : 0
+      d2[0].y = __hiloint2double(__double2hiint(c2[0].y) > 0 ? 0x3ff00000 : 0, 0);  // b > 0 ? +1 : 0
+      d2[1].x = -2.0 * c2[0].x;            d2[1].y = 2.0 * c2[0].y;
+      d2[2].x = -4.0 * (c2[0].x * c2[1].x); d2[2].y = 4.0 * (c2[0].y * c2[1].y);
+#pragma unroll
+      for (int zi = 0; zi < 4; zi++)
       {
-        const double2 c2 = *reinterpret_cast<const double2*>(sc + 12 + e);
-        const double2 d2 = *reinterpret_cast<const double2*>(sc + 20 + e);
-        phi[e] = fma(c2.x, eF, phi[e]);
-        phi[e + 1] = fma(c2.y, eF, phi[e + 1]);
+        const int e = 2 * zi;
+        phi[e] = fma(c2[zi].x, eF, phi[e]);
+        phi[e + 1] = fma(c2[zi].y, eF, phi[e + 1]);
         if (GRAD)
         {
-          acc[e][0] = fma(c2.x, v2x, fma(d2.x, v1x, acc[e][0]));
-          acc[e][1] = fma(c2.x, v2y, fma(d2.x, v1y, acc[e][1]));
-          acc[e][2] = fma(c2.x, v2z, fma(d2.x, v1z, acc[e][2]));
-          acc[e + 1][0] = fma(c2.y, v2x, fma(d2.y, v1x, acc[e + 1][0]));
-          acc[e + 1][1] = fma(c2.y, v2y, fma(d2.y, v1y, acc[e + 1][1]));
-          acc[e + 1][2] = fma(c2.y, v2z, fma(d2.y, v1z, acc[e + 1][2]));
+          acc[e][0] = fma(c2[zi].x, v2x, fma(d2[zi].x, v1x, acc[e][0]));
+          acc[e][1] = fma(c2[zi].x, v2y, fma(d2[zi].x, v1y, acc[e][1]));
+          acc[e][2] = fma(c2[zi].x, v2z, fma(d2[zi].x, v1z, acc[e][2]));
+          acc[e + 1][0] = fma(c2[zi].y, v2x, fma(d2[zi].y, v1x, acc[e + 1][0]));
+          acc[e + 1][1] = fma(c2[zi].y, v2y, fma(d2[zi].y, v1y, acc[e + 1][1]));
+          acc[e + 1][2] = fma(c2[zi].y, v2z, fma(d2[zi].y, v1z, acc[e + 1][2]));
         }
       }
     };
@@ -536,18 +547,18 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
           sc[5] = a * ukx + b * wx;           sc[6] = a * uky + b * wy;           sc[7] = a * ukz + b * wz;
           sc[8] = dF_ik * ukx + dF_jk * wx;   sc[9] = dF_ik * uky + dF_jk * wy;   sc[10] = dF_ik * ukz + dF_jk * wz;
 #pragma unroll
-          for (int si2 = 0; si2 < 2; si2++)  // (1 +- cos)^{1,2,4,16} and derivative factors, :749-767
+          for (int si2 = 0; si2 < 2; si2++)  // (1 +- cos)^{1,2,4,16} and 16 lambda (1 +- cos)^15, :749-767
           {
             const double lam = si2 ? 1.0 : -1.0;
             double bse = fma(lam, ct, 1.0);
-            const bool ok = bse > 0.0;  // guard of :755-767
-            bse = ok ? bse : 0.0;
+            bse = bse > 0.0 ? bse : 0.0;  // guard of :755-767
             const double b2 = bse * bse, b3 = b2 * bse, b4 = b2 * b2, b8 = b4 * b4;
             const double b16 = b8 * b8, b15 = b8 * b4 * b3;
-            sc[12 + 0 + si2] = bse; sc[20 + 0 + si2] = ok ? lam : 0.0;
-            sc[12 + 2 + si2] = b2;  sc[20 + 2 + si2] = 2.0 * lam * bse;
-            sc[12 + 4 + si2] = b4;  sc[20 + 4 + si2] = 4.0 * lam * b3;
-            sc[12 + 6 + si2] = b16; sc[20 + 6 + si2] = 16.0 * lam * b15;
+            sc[12 + 0 + si2] = bse;
+            sc[12 + 2 + si2] = b2;
+            sc[12 + 4 + si2] = b4;
+            sc[12 + 6 + si2] = b16;
+            sc[20 + si2] = 16.0 * lam * b15;
           }
         }
         else
@@ -732,9 +743,13 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
       e_ = cudaFuncSetAttribute(symfun_sweep_kernel<G, T>,                                             \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem);        \
     if (e_ != cudaSuccess) { rc = -(int) e_; break; }                                                  \
+    kb_timing_begin(KB_T_PREP, st);                                                                    \
     symfun_prep_kernel<G, T><<<pgrid, PREP_WARPS * 32, prep_warp * PREP_WARPS, st>>>(P, A,             \
                                                                                      (int) prep_warp); \
+    kb_timing_end(KB_T_PREP, st);                                                                      \
+    kb_timing_begin(KB_T_SWEEP, st);                                                                   \
     symfun_sweep_kernel<G, T><<<sgrid, 32, sweep_smem, st>>>(P, A);                                    \
+    kb_timing_end(KB_T_SWEEP, st);                                                                     \
   } while (0)
   for (int c = 0; c < n_chunks && rc == KB_OK; c++)
   {

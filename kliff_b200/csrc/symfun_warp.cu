@@ -569,7 +569,9 @@ int kb_symfun_warp_launch(const kb_symfun_params& P, int n_centers, const int32_
   do {                                                                                              \
     KB_CUDA(cudaFuncSetAttribute(symfun_warp_kernel<G, T>,                                          \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));         \
+    kb_timing_begin(KB_T_FUSED, st);                                                                \
     symfun_warp_kernel<G, T><<<grid, 32, smem, st>>>(P, A);                                         \
+    kb_timing_end(KB_T_FUSED, st);                                                                  \
   } while (0)
   if (!grad) KB_WARP_LAUNCH(false, double);
   else if (dz_dtype == KB_F32) KB_WARP_LAUNCH(true, float);

@@ -351,3 +351,12 @@ def probe_hbm_copy(nbytes=1 << 30):
 def launch_count(reset=False):
     """Kernels launched by libkliff_b200 in this process so far."""
     return int(_lib.lib().kb_launch_count(1 if reset else 0))
+
+
+def kernel_timing(enable):
+    """Collects the per-kernel device times recorded since the last call and switches recording
+    on/off.  Returns {"prep": (ms, launches), "sweep": (...), "fused": (...)}."""
+    ms = (C.c_double * 3)()
+    cnt = (C.c_int32 * 3)()
+    check(_lib.lib().kb_kernel_timing(int(bool(enable)), ms, cnt), "kb_kernel_timing")
+    return {name: (ms[q], cnt[q]) for q, name in enumerate(("prep", "sweep", "fused"))}
