@@ -31,7 +31,7 @@ BYTES_CANON = 36724.0   # per atom, fp64 zeta + dG/dr written + inputs read once
 # dram__bytes_read.sum + dram__bytes_write.sum of the descriptor stage on this very workload
 # (1 000 000 atoms: 4 chunks x (symfun_prep_kernel + symfun_sweep_kernel)), ncu --set full capture
 # of round 1: profiles/r01_ncu_symfun_split_1M_traffic.txt
-TRAFFIC_NCU_BYTES_PER_ATOM = None
+TRAFFIC_NCU_BYTES_PER_ATOM = 82207.7
 
 
 def diamond(nx, seed):
@@ -520,7 +520,9 @@ def main():
                                  if (args.nx == 50 and TRAFFIC_NCU_BYTES_PER_ATOM) else None),
                      "traffic_source": "ncu capture profiles/r01_ncu_symfun_split_1M_traffic.txt (bytes per step: all launches of the stage)",
                      "peak_source": peak_src,
-                     "note": "algorithmic bytes 36 724 B/atom; the kernel is FP64-pipe bound, see roofline_fp64"},
+                     "note": "algorithmic bytes 36 724 B/atom; traffic adds the per-atom records handed from the "
+                             "table kernel to the sweep kernel (2 x 10.4 KB) and sector fills of the 24-byte row "
+                             "writes; the stage is bound by the FP64 and shared-memory pipes, see roofline_fp64"},
         "roofline_fp64": {"kernel": kname, "bound": "fp64", "achieved": ach_tf,
                           "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                           "peak_source": "DFMA-chain probe in this run (kb_probe_fp64_peak)",

@@ -567,3 +567,22 @@ def test_batched_descriptor_equals_per_configuration(dev):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert np.array_equal(a.atom_ptr, b.atom_ptr) and np.array_equal(a.cfg_ptr, b.cfg_ptr)
     assert a.maxn == b.maxn
+
+
+def test_kernel_timing_records_stage_launches(dev):
+    """kb_kernel_timing brackets the descriptor kernels with CUDA events on their stream (what
+    bench.py's roofline uses): AUTO = one table launch + one sweep launch for a small system."""
+    g = load_golden("ref_run_si64_set51.npz")
+    rc = float(np.max(g["rcut"]))
+    r = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], rc)
+    P = ops.build_params(get_set51(), np.array([[rc]]))
+    code = torch.zeros(r["allc"].shape[0], dtype=torch.int32, device=dev)
+    ops.kernel_timing(True)
+    ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"], n_centers=r["n"])
+    ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"], n_centers=r["n"],
+                       mode=_lib.KB_SYMFUN_WARP)
+    t = ops.kernel_timing(False)
+    assert t["prep"][1] == 1 and t["sweep"][1] == 1 and t["fused"][1] == 1
+    assert all(0.0 < t[k][0] < 1000.0 for k in ("prep", "sweep", "fused"))
+    ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"], n_centers=r["n"])
+    assert ops.kernel_timing(False)["sweep"][1] == 0  # recording is off again
