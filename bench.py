@@ -460,10 +460,11 @@ def main():
     f_host = torch.empty(3 * n, dtype=torch.float64).pin_memory()
 
     def e2e_step():
-        packed = desc.transform_packed([conf], grad=True, device=dev)
+        # descriptors stream to the pinned host array piece by piece while the kernels run
+        packed = desc.transform_packed([conf], grad=True, device=dev, zeta_host=zeta_host)
         F = packed.forces(w, 0, n)
-        zeta_host.copy_(packed.zeta, non_blocking=True)
         f_host.copy_(F, non_blocking=True)
+        packed.host_ready.synchronize()
         torch.cuda.synchronize()
         return packed
 
@@ -529,8 +530,9 @@ def main():
                           "note": "canonical 380 618 flop/atom (SURVEY.md §8d)"},
         "e2e": {"value": e2e_value, "unit": "atoms/s", "h2d_bytes_per_step": int(24 * n),
                 "d2h_bytes_per_step": int(8 * n * D + 24 * n),
-                "what": "SymmetryFunction.transform_packed(Configuration with pinned host coords) + "
-                        "force contraction; zeta and forces copied back to pinned host memory"},
+                "what": "SymmetryFunction.transform_packed(Configuration with pinned host coords, "
+                        "zeta_host=pinned array) + force contraction; zeta (streamed per 262 144-atom piece "
+                        "on a side stream) and forces copied back to pinned host memory"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -104,10 +104,12 @@ class SymmetryFunction(Descriptor):
         return dict(coords=d["coords"], code=code, image_local=d["image"], counts=d["counts"],
                     indices_local=d["indices"], n_contrib=n, maxn=d["maxn"]), nei
 
-    def transform_packed(self, configs, grad=True, device=None, gradient_dtype=np.float64):
+    def transform_packed(self, configs, grad=True, device=None, gradient_dtype=np.float64, zeta_host=None):
         """Descriptors (+ packed dG/dr) of a list of configurations in one batched pass.
         `gradient_dtype` is the storage type of the blocks (fp64 unless asked otherwise;
-        `generate_fingerprints` passes the descriptor's `dtype`, as the reference casts there)."""
+        `generate_fingerprints` passes the descriptor's `dtype`, as the reference casts there).
+        `zeta_host`: optional pinned host array [N, D] the raw descriptors are streamed into while
+        the kernels run (`packed.host_ready` is the event to wait for)."""
         device = device if device is not None else default_device()
         if not isinstance(configs, (list, tuple)):
             configs = [configs]
@@ -123,7 +125,8 @@ class SymmetryFunction(Descriptor):
             parts = [self._config_part(c, device)[0] for c in configs]
             packed = PackedFingerprints.from_parts(len(self), device, parts)
         packed.compute(self._params, grad=grad, mode=self.kernel_mode,
-                       dz_dtype=torch.float32 if gradient_dtype in (np.float32, torch.float32) else torch.float64)
+                       dz_dtype=torch.float32 if gradient_dtype in (np.float32, torch.float32) else torch.float64,
+                       zeta_host=zeta_host)
         return packed
 
     def transform(self, conf, fit_forces=False, fit_stress=False):

@@ -38,14 +38,11 @@ class NeighborList:
         coords_cb = np.ascontiguousarray(self.conf.coords, dtype=np.double).reshape(-1, 3)
         cell = np.asarray(self.conf.cell, dtype=np.double)
         pbc = np.asarray(self.conf.PBC, dtype=np.intc)
-        try:
-            z_cb = map_species(self.conf.species, atomic_number)
-        except KeyError as e:
-            raise NeighborListError(f"unknown chemical species {e}")
+        # species play no role in the neighbor build: paddings inherit the species of the atom they
+        # are an image of (neighbor_list.cpp:407-408), looked up lazily through `pad_image`
         d_coords = torch.as_tensor(coords_cb, device=dev)
-        d_z = torch.as_tensor(z_cb, device=dev)
         try:
-            pc, pz, pi = ops.create_paddings(self.infl_dist, cell, pbc, d_coords, d_z)
+            pc, _, pi = ops.create_paddings(self.infl_dist, cell, pbc, d_coords, None)
         except KliffB200Error as e:
             if e.code == KB_ERR_REFERENCE:
                 raise NeighborListError("Calling `neighlist.create_paddings` failed.")
@@ -62,9 +59,9 @@ class NeighborList:
             if e.code == KB_ERR_REFERENCE:
                 raise NeighborListError("Calling `neighlist.build` failed.")
             raise
-        self.device_data = dict(coords=allc, z=torch.cat([d_z, pz]), image=image, counts=counts,
+        self.device_data = dict(coords=allc, image=image, counts=counts,
                                 offsets=offsets, indices=indices, maxn=maxn, n_contrib=num_cb,
-                                pad_coords=pc, pad_z=pz, pad_image=pi)
+                                pad_coords=pc, pad_image=pi)
         self._host = {}
 
     # ------------------------------------------------------------------ lazy host mirrors
@@ -93,7 +90,11 @@ class NeighborList:
 
     @property
     def padding_species(self):
-        return [atomic_species[int(i)] for i in self._h("pad_z")]
+        sp = np.asarray(self.conf.species)
+        for name in np.unique(sp):
+            if str(name) not in atomic_number:
+                raise NeighborListError(f"unknown chemical species {name}")
+        return [str(x) for x in sp[self._h("pad_image")]]
 
     @property
     def padding_image(self):

@@ -231,10 +231,14 @@ def block_offsets(n_centers, centers, offsets, n_desc):
 
 
 def symfun_forward(params, coords, species, offsets, indices, maxn, n_centers=None, centers=None,
-                   grad=True, mode=_lib.KB_SYMFUN_AUTO, dz_ptr=None, dz=None, dz_dtype=torch.float64):
+                   grad=True, mode=_lib.KB_SYMFUN_AUTO, dz_ptr=None, dz=None, dz_dtype=torch.float64,
+                   zeta_out=None):
     """Descriptors (and packed dG/dr) of centre atoms.  Returns (zeta f64[n_centers, D],
     dz [total] | None, dz_ptr i64[n_centers+1] | None).  Arithmetic is fp64; `dz_dtype` float32
-    rounds the finished blocks on the way out (half the memory and contraction traffic)."""
+    rounds the finished blocks on the way out (half the memory and contraction traffic).
+    `zeta_out` (contiguous cuda f64 [n_centers, D], e.g. a row range of a larger array) receives the
+    descriptors instead of a fresh allocation; with `dz_ptr` a slice of a batch-wide offset array
+    this lets a caller run a long centre list in pieces (PackedFingerprints.compute)."""
     _need_cuda(coords, species, offsets, indices, centers)
     if centers is not None:
         n_centers = centers.shape[0]
@@ -242,7 +246,13 @@ def symfun_forward(params, coords, species, offsets, indices, maxn, n_centers=No
         raise ValueError("n_centers or centers required")
     D = params.n_desc
     dev = coords.device
-    zeta = torch.empty((n_centers, D), dtype=torch.float64, device=dev)
+    if zeta_out is not None:
+        if (not zeta_out.is_cuda or zeta_out.dtype != torch.float64 or not zeta_out.is_contiguous()
+                or tuple(zeta_out.shape) != (n_centers, D)):
+            raise ValueError("zeta_out must be a contiguous cuda float64 [n_centers, D] tensor")
+        zeta = zeta_out
+    else:
+        zeta = torch.empty((n_centers, D), dtype=torch.float64, device=dev)
     if grad:
         if dz_ptr is None:
             dz_ptr, total = block_offsets(n_centers, centers, offsets, D)

@@ -139,11 +139,53 @@ class PackedFingerprints:
         self.cfg_ptr = cfg_ptr
         return self
 
-    def compute(self, params, grad=True, mode=0, dz_dtype=torch.float64):
-        """Run the descriptor kernel over every centre atom (one launch)."""
-        self.zeta, self.dz, self.dz_ptr = ops.symfun_forward(
-            params, self.coords, self.code, self.offsets, self.indices, self.maxn,
-            centers=self.centers, grad=grad, mode=mode, dz_dtype=dz_dtype)
+    def compute(self, params, grad=True, mode=0, dz_dtype=torch.float64, zeta_host=None,
+                piece=1 << 18):
+        """Run the descriptor kernels over every centre atom.
+
+        `zeta_host` (pinned host f64 [n_centers, D]): stream the descriptors to the host while the
+        kernels are still working — the centre list is processed in pieces and each piece's rows
+        are copied device->host on a side stream as soon as that piece is done, so the PCIe time
+        (8 D bytes per atom) hides behind the next piece's compute.  `self.host_ready` is the event
+        to wait for before reading `zeta_host`."""
+        self.host_ready = None
+        n = self.n_centers
+        if zeta_host is None or n <= piece:
+            self.zeta, self.dz, self.dz_ptr = ops.symfun_forward(
+                params, self.coords, self.code, self.offsets, self.indices, self.maxn,
+                centers=self.centers, grad=grad, mode=mode, dz_dtype=dz_dtype)
+            if zeta_host is not None:
+                zeta_host.copy_(self.zeta, non_blocking=True)
+                self.host_ready = torch.cuda.Event()
+                self.host_ready.record()
+            return self
+        if tuple(zeta_host.shape) != (n, self.D) or zeta_host.dtype != torch.float64 or not zeta_host.is_pinned():
+            raise ValueError("zeta_host must be a pinned float64 [n_centers, D] host tensor")
+        dev = self.coords.device
+        self.zeta = torch.empty((n, self.D), dtype=torch.float64, device=dev)
+        if grad:
+            self.dz_ptr, total = ops.block_offsets(n, self.centers, self.offsets, self.D)
+            self.dz = torch.empty((total,), dtype=dz_dtype, device=dev)
+        else:
+            self.dz = self.dz_ptr = None
+        main = torch.cuda.current_stream()
+        side = getattr(PackedFingerprints, "_side_stream", None)
+        if side is None or side.device != dev:
+            side = PackedFingerprints._side_stream = torch.cuda.Stream(device=dev)
+        for lo in range(0, n, piece):
+            hi = min(n, lo + piece)
+            ops.symfun_forward(params, self.coords, self.code, self.offsets, self.indices, self.maxn,
+                               centers=self.centers[lo:hi], grad=grad, mode=mode,
+                               dz_ptr=self.dz_ptr[lo:hi + 1] if grad else None, dz=self.dz,
+                               zeta_out=self.zeta[lo:hi])
+            done = torch.cuda.Event()
+            done.record(main)
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                zeta_host[lo:hi].copy_(self.zeta[lo:hi], non_blocking=True)
+        self.zeta.record_stream(side)
+        self.host_ready = torch.cuda.Event()
+        self.host_ready.record(side)
         return self
 
     # ------------------------------------------------------------------ per-configuration views

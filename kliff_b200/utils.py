@@ -54,11 +54,34 @@ def default_device():
 
 def map_species(species, mapping, what="species"):
     """Vectorised `[mapping[s] for s in species]` -> int32 array (a 1M-atom configuration must
-    not cost a million dict lookups)."""
+    not cost a million dict lookups, nor a million string comparisons: fixed-width unicode arrays of
+    up to two characters are compared as integers)."""
     arr = np.asarray(species)
-    out = np.full(arr.shape[0], -1, dtype=np.int32)
+    out = np.empty(arr.shape[0], dtype=np.int32)
+    out.fill(-1)
     if arr.shape[0] == 0:
         return out
+    if arr.dtype.kind == "U" and arr.dtype.itemsize in (4, 8) and arr.ndim == 1:
+        keys = np.ascontiguousarray(arr).view(np.uint32 if arr.dtype.itemsize == 4 else np.uint64)
+        if not (keys != keys[0]).any():  # one species (the common large case): two passes over the array
+            name = str(arr[0])
+            if name not in mapping:
+                raise KeyError(name)
+            out.fill(mapping[name])
+            return out
+        pos, seen = 0, 0
+        while seen <= 128:
+            k = keys[pos]
+            name = str(np.array([k], dtype=keys.dtype).view(arr.dtype)[0])
+            if name not in mapping:
+                raise KeyError(name)
+            np.putmask(out, keys == k, mapping[name])
+            seen += 1
+            left = out < 0
+            if not left.any():
+                return out
+            pos = int(left.argmax())
+        out[:] = -1
     for name in np.unique(arr) if arr.shape[0] < 4096 else _unique_large(arr):
         if str(name) not in mapping:
             raise KeyError(str(name))

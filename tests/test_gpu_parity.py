@@ -586,3 +586,30 @@ def test_kernel_timing_records_stage_launches(dev):
     assert all(0.0 < t[k][0] < 1000.0 for k in ("prep", "sweep", "fused"))
     ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"], n_centers=r["n"])
     assert ops.kernel_timing(False)["sweep"][1] == 0  # recording is off again
+
+
+def test_streamed_host_descriptors_equal_single_pass(dev):
+    """PackedFingerprints.compute(zeta_host=...) runs the centre list in pieces and streams each
+    piece's descriptors to pinned host memory on a side stream: same zeta, same blocks."""
+    from helpers import configs_from_npz
+    from kliff_b200.legacy.descriptors.symmetry_function import SymmetryFunction
+    from kliff_b200.packed import PackedFingerprints
+    desc = SymmetryFunction({"Si-Si": 5.0, "Si-C": 4.5, "C-C": 4.0}, "cos", "set51")
+    confs = configs_from_npz("sic_training_set.npz", limit=4) + configs_from_npz("si_varying_alat.npz", limit=3)
+    ref = desc.transform_packed(confs, grad=True, device=dev)
+    n = ref.n_centers
+    host = torch.empty((n, len(desc)), dtype=torch.float64).pin_memory()
+    host.fill_(-1.0)
+    p = PackedFingerprints.from_configs(len(desc), dev, confs, desc.species_code, 5.0)
+    p.compute(desc._params, grad=True, zeta_host=host, piece=50)
+    p.host_ready.synchronize()
+    assert torch.equal(p.zeta, ref.zeta) and torch.equal(p.dz_ptr, ref.dz_ptr)
+    assert torch.equal(host, ref.zeta.cpu())
+    # blocks: compare the used part of every block (alignment padding of the last block of a piece
+    # is zero-filled by whichever call owns it)
+    assert torch.equal(p.dz, ref.dz)
+    # the one-piece path fills the host array too
+    host.fill_(-1.0)
+    q = desc.transform_packed(confs, grad=False, device=dev, zeta_host=host)
+    q.host_ready.synchronize()
+    assert torch.equal(host, ref.zeta.cpu())
