@@ -91,6 +91,7 @@ struct SplitArgs
   int32_t* work;          // sweep: dynamic work counter of this chunk
   unsigned char* records; // [hi - lo] records
   int NP, RC, NGP;
+  int ang_lo, ang_hi;     // descriptor rows [ang_lo, ang_hi) are exactly the angular sets (else 0, 0)
 };
 
 __host__ __device__ inline size_t prep_smem_bytes(const kb_symfun_params& P, int NP, int RC)
@@ -459,6 +460,16 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
     const int row = 3 * (n + 1);
     TOut* blk = GRAD ? static_cast<TOut*>(A.dz) + A.dz_ptr[t] : nullptr;
     double* zrow = A.zeta + (int64_t) t * D;
+    if (GRAD && A.ang_hi > A.ang_lo)
+    {
+      // (optional, KB_PREZERO=1) Zero the angular rows with full, coalesced sector writes first.  The row pieces written
+      // below are 24 bytes at 8-byte alignment, i.e. partial 32-byte sectors: a partial write to a
+      // sector that is not in L2 makes L2 fetch it from DRAM (ncu: 13.5 KB of reads per atom that the
+      // algorithm never asks for); after this pass every later piece lands on a resident dirty line.
+      TOut* z0 = blk + (unsigned) (A.ang_lo * row);
+      const int len = (A.ang_hi - A.ang_lo) * row;
+      for (int q = lane; q < len; q += 32) z0[q] = (TOut) 0;
+    }
     __syncwarp();
 
     // ---- phase E: triple loop (see symfun_warp.cu for the derivation) ---------------------------
@@ -723,6 +734,27 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
   A.centers = d_centers; A.subset = d_subset; A.coords = d_coords; A.species = d_species;
   A.nl_off = d_nl_off; A.nl_idx = d_nl_idx; A.zeta = d_zeta; A.dz = d_dz; A.dz_ptr = d_dz_ptr;
   A.overflow = d_overflow; A.records = records; A.NP = NP; A.RC = RC; A.NGP = NGP;
+  {
+    // angular rows as one contiguous range with no radial row inside (true for set51 / set30)
+    int lo = P.n_desc, hi = 0, cnt = 0;
+    for (int g = 0; g < P.n_groups; g++)
+      for (int e = 0; e < GW; e++)
+        if (P.grp_out[g][e] >= 0)
+        {
+          lo = P.grp_out[g][e] < lo ? P.grp_out[g][e] : lo;
+          hi = P.grp_out[g][e] + 1 > hi ? P.grp_out[g][e] + 1 : hi;
+          cnt++;
+        }
+    const bool contiguous = cnt > 0 && hi - lo == cnt;
+    A.ang_lo = contiguous ? lo : 0;
+    A.ang_hi = contiguous ? hi : 0;
+    // Off by default: it removes the stage's excess DRAM traffic (82.2 -> 60.3 KB per atom at 1M atoms,
+    // profiles/r01_ncu_symfun_split_1M_traffic.txt) but costs 2.8 % of sweep time, because the extra
+    // 30 KB per atom go through the L1/shared data pipe, which is this kernel's tightest unit while
+    // DRAM is only 29 % busy.  KB_PREZERO=1 switches it on.
+    const char* pz = getenv("KB_PREZERO");
+    if (!(pz && pz[0] == '1')) A.ang_lo = A.ang_hi = 0;
+  }
 
   int per_sm = (int) (limit / (sweep_smem + per_block_reserve));
   if (per_sm > want) per_sm = want;
