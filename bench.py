@@ -360,6 +360,16 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # cpu_baseline and the train_epoch probe are N=1 extras (rank 0 of a single-process run).  The
+    # baseline's worker pool is forked HERE, before CUDA / NCCL exist in this process: forking a process
+    # that already holds a CUDA context and NCCL watchdog threads can deadlock the children.
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline and args.workload == "supercell":
+        try:
+            cpu_base = CpuBaseline(nx=12)
+        except Exception as e:
+            cpu_base = e
+
     import torch
     import torch.distributed as dist
 
@@ -536,14 +546,16 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    if args.epoch_configs > 0:
+    if args.epoch_configs > 0 and world == 1:
         try:
             line["train_epoch"] = train_epoch_probe(args.epoch_configs, dev)
         except Exception as e:  # reported, never required
             line["train_epoch"] = {"error": str(e)}
-    if not args.no_cpu_baseline:
+    if cpu_base is not None:
         try:
-            base = CpuBaseline(nx=12)
+            if isinstance(cpu_base, Exception):
+                raise cpu_base
+            base = cpu_base
             sample = int(max(2000, min(200000, 470.0 * base.cores * 12.0)))
             base.run(base.cores * 8)
             rate = base.run(sample)
