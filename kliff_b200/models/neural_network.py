@@ -103,3 +103,100 @@ class NeuralNetwork(ModelTorch):
         for layer in self.layers:
             x = layer(x)
         return x
+
+    # ------------------------------------------------------------------ KIM / DUNN export
+    # File formats of neural_network.py:83-330 (read by the DUNN model driver).  Layers must come
+    # as [Dropout]? (Linear Activation [Dropout]?)* Linear, as there.
+    _ACTIVATIONS = {"Sigmoid": "sigmoid", "Tanh": "tanh", "ReLU": "relu", "ELU": "elu"}
+
+    def _kim_groups(self):
+        """-> (linears, activation name, keep probabilities per Linear input)."""
+        if not self.layers:
+            raise NeuralNetworkError("no layers to write; call `add_layers()` first")
+        linears, acts, keep, pending_drop, prev = [], [], [], 0.0, None
+        for i, layer in enumerate(self.layers):
+            name = layer.__class__.__name__
+            if name == "Linear":
+                linears.append(layer)
+                keep.append(1.0 - pending_drop)
+                pending_drop = 0.0
+            elif name in self._ACTIVATIONS:
+                if prev != "Linear":
+                    raise NeuralNetworkError(
+                        f"Cannot convert to KIM model. a `{name}` layer must follow a \"Linear\" layer.")
+                acts.append(self._ACTIVATIONS[name])
+            elif name.startswith("Dropout"):
+                if i != 0 and prev not in self._ACTIVATIONS:
+                    raise NeuralNetworkError(
+                        f"Cannot convert to KIM model. a `{name}` layer must follow an activation layer.")
+                pending_drop = float(layer.p)
+            else:
+                raise NeuralNetworkError(f"Layer `{name}` not supported by KIM model. Cannot proceed to write.")
+            prev = name
+        if prev != "Linear" or len(acts) != len(linears) - 1:
+            raise NeuralNetworkError("Cannot convert to KIM model: the last layer must be `Linear` and every "
+                                     "other `Linear` layer needs an activation.")
+        if len(set(acts)) > 1:
+            raise NeuralNetworkError("KIM model supports a single activation function type")
+        return linears, (acts[0] if acts else "tanh"), keep
+
+    def write_kim_model(self, path=None, driver_name="DUNN__MD_292677547454_000", dropout_ensemble_size=None):
+        if path is None:
+            path = Path.cwd() / "NeuralNetwork_KLIFF__MO_000000111111_000"
+        path = Path(path).expanduser().resolve()
+        path.mkdir(parents=True, exist_ok=True)
+        files = ["descriptor.params", "NN.params", "dropout_binary.params"]
+        linears, activation, keep = self._kim_groups()
+        bar = "#" + "=" * 80 + "\n"
+        num = "{:23.15e}" if self.dtype == torch.float64 else "{:15.7e}"
+
+        with open(path / "CMakeLists.txt", "w") as f:
+            f.write("#\n# Contributors:\n#    KLIFF (https://kliff.readthedocs.io)\n#\n\n"
+                    "cmake_minimum_required(VERSION 3.4)\n\n"
+                    "list(APPEND CMAKE_PREFIX_PATH $ENV{KIM_API_CMAKE_PREFIX_DIR})\n"
+                    "find_package(KIM-API 2.0 REQUIRED CONFIG)\n"
+                    "if(NOT TARGET kim-api)\n  enable_testing()\n"
+                    '  project("${KIM_API_PROJECT_NAME}" VERSION "${KIM_API_VERSION}"\n'
+                    "    LANGUAGES CXX C Fortran)\nendif()\n\n"
+                    "add_kim_api_model_library(\n"
+                    f'  NAME            "{path.name}"\n  DRIVER_NAME     "{driver_name}"\n'
+                    "  PARAMETER_FILES" + "".join(f' "{s}"' for s in files) + "\n  )\n")
+
+        with open(path / files[1], "w") as f:
+            f.write(bar + "# NN structure and parameters file generated by KLIFF\n# \n"
+                    '# Note that the NN assumes each row of the input "X" is an \n'
+                    "# observation, i.e. the layer is implemented as\n# Y = activation(XW + b).\n"
+                    '# You need to transpose your weight matrix if each column of "X" is \n'
+                    "# an observation.\n" + bar + "\n")
+            f.write(f"{len(linears)}    # number of layers (excluding input layer,including output layer)\n")
+            f.write("".join(f"{la.out_features}  " for la in linears) + "  # size of each layer (last must be 1)\n")
+            f.write(f"{activation}    # activation function\n")
+            f.write("".join("{:.15g}  ".format(k) for k in keep) + "  # keep probability of input for each layer\n\n")
+            for i, la in enumerate(linears):
+                w = la.weight.detach().cpu().t()  # torch stores W^T (y = x W^T + b)
+                b = la.bias.detach().cpu()
+                last = i == len(linears) - 1
+                f.write("# weight of output layer, shape({}, {})\n".format(*w.shape) if last else
+                        "# weight of hidden layer {},  shape({}, {})\n".format(i + 1, *w.shape))
+                for row in w:
+                    f.write("".join(num.format(float(x)) for x in row) + "\n")
+                f.write("# bias of output layer, shape({}, )\n".format(w.shape[1]) if last else
+                        "# bias of hidden layer {}, shape({}, )\n".format(i + 1, w.shape[1]))
+                f.write("".join(num.format(float(x)) for x in b) + "\n\n")
+
+        self.descriptor.write_kim_params(path, files[0])
+
+        drop = [1.0 - k for k in keep]
+        size = 0 if all(d < 1e-10 for d in drop) else (100 if dropout_ensemble_size is None else dropout_ensemble_size)
+        units = [self.descriptor.get_size()] + [la.out_features for la in linears]
+        with open(path / files[2], "w") as f:
+            f.write(bar + "# Dropout binary parameters file generated by KLIFF.\n#\n"
+                    '# Note, "ensemble size = 0", means that no dropout needs to be\n'
+                    "# applied at all." + bar + "\n")
+            f.write(f"{size}  # ensemble size\n")
+            for rep in range(size):
+                f.write(bar + f"# instance {rep}\n")
+                for i, k in enumerate(keep):
+                    mask = np.clip(np.floor(np.random.uniform(k, k + 1, units[i])).astype(np.intc), 0, 1)
+                    f.write(f"# layer {i}\n" + "".join(f"{d} " for d in mask) + "\n")
+        return path

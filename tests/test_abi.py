@@ -68,3 +68,47 @@ def test_no_cpu_fallback():
     import torch
     with pytest.raises(RuntimeError, match="no CPU implementation"):
         ops.create_paddings(3.0, np.eye(3), [1, 1, 1], torch.zeros((2, 3), dtype=torch.float64))
+
+
+def test_write_kim_model_files_round_trip(tmp_path):
+    """KIM/DUNN export (neural_network.py:83-330 layouts): NN.params parses back to the layers'
+    weights (transposed, row per input) and keep probabilities; descriptor.params and the CMake
+    stub name the three parameter files.  Host-only: no kernel is involved."""
+    import numpy as np
+    import torch
+
+    from kliff_b200.legacy import nn
+    from kliff_b200.legacy.descriptors import SymmetryFunction
+    from kliff_b200.models import NeuralNetwork
+    from kliff_b200.models.neural_network import NeuralNetworkError
+
+    desc = SymmetryFunction({"Si-Si": 5.0}, "cos", "set30", normalize=False, dtype=np.float64)
+    model = NeuralNetwork(desc)
+    model.add_layers(nn.Linear(30, 6), nn.Tanh(), nn.Dropout(0.25), nn.Linear(6, 4), nn.Tanh(), nn.Linear(4, 1))
+    out = model.write_kim_model(tmp_path / "NN_roundtrip__MO_000000111111_000", dropout_ensemble_size=2)
+    assert sorted(p.name for p in out.iterdir()) == ["CMakeLists.txt", "NN.params", "descriptor.params",
+                                                     "dropout_binary.params"]
+    lines = [ln.split("#")[0].split() for ln in open(out / "NN.params")]
+    rows = [ln for ln in lines if ln]
+    assert rows[0] == ["3"] and rows[1] == ["6", "4", "1"] and rows[2] == ["tanh"]
+    assert [float(x) for x in rows[3]] == [1.0, 0.75, 1.0]
+    pos = 4
+    for layer in (model.layers[0], model.layers[3], model.layers[5]):
+        w = layer.weight.detach().numpy().T
+        got = np.array([[float(x) for x in r] for r in rows[pos:pos + w.shape[0]]])
+        assert np.allclose(got, w, rtol=1e-14, atol=0)
+        pos += w.shape[0]
+        assert np.allclose([float(x) for x in rows[pos]], layer.bias.detach().numpy(), rtol=1e-14, atol=0)
+        pos += 1
+    assert pos == len(rows)
+    drop = [ln.split("#")[0].split() for ln in open(out / "dropout_binary.params")]
+    drop = [d for d in drop if d]
+    assert drop[0] == ["2"] and [len(d) for d in drop[1:]] == [30, 6, 4, 30, 6, 4]
+    assert 'PARAMETER_FILES "descriptor.params" "NN.params" "dropout_binary.params"' in open(out / "CMakeLists.txt").read()
+    bad = NeuralNetwork(desc)
+    bad.add_layers(nn.Linear(30, 4), nn.Linear(4, 1))
+    try:
+        bad.write_kim_model(tmp_path / "bad")
+        assert False, "two Linear layers in a row must be refused"
+    except NeuralNetworkError:
+        pass
