@@ -105,6 +105,13 @@ class LossNeuralNetworkModel:
         self._epoch = 0
         self.vectorized = True
         self.epoch_losses = []
+        # One CUDA graph per batch (captured the first time the batch is met, replayed afterwards):
+        # a 100-configuration step is ~150 tiny launches whose host-side issue time (1.5 ms) is 5x
+        # their device time.  Single-GPU vectorised route only; KB_NO_GRAPHS=1 switches it off.
+        self.use_cuda_graphs = os.environ.get("KB_NO_GRAPHS", "0") != "1"
+        self._graphs = {}
+        self._graph_pool = None
+        self._graph_acc = None
 
     # ------------------------------------------------------------------ minimize (loss.py:740-828)
     def minimize(self, method="Adam", batch_size=100, num_epochs=1000, start_epoch=0, **kwargs):
@@ -125,11 +132,17 @@ class LossNeuralNetworkModel:
         dist = _dist()
         chief = dist is None or dist.get_rank() == 0
         self.epoch_losses = []
+        self._graphs, self._graph_pool, self._graph_acc = {}, None, None  # graphs belong to one optimizer
+        graphed = self._graphs_possible(method, kwargs) and self._prepare_graphs(method, kwargs)
         epoch = 0
         for epoch in range(self.start_epoch, self.start_epoch + self.num_epochs):
             self._epoch = epoch
             if self.start_epoch != 0 and epoch == self.start_epoch:
                 epoch_loss = self._get_loss_epoch(loader)
+            elif graphed:
+                epoch_loss = self._graphed_pass(train=True)
+                if chief:
+                    self.calculator.save_model(epoch)
             else:
                 epoch_loss = 0
                 for batch in self._batches(loader):
@@ -167,13 +180,105 @@ class LossNeuralNetworkModel:
             for batch in loader:
                 yield batch
 
+    # ------------------------------------------------------------------ CUDA-graph stepping
+    def _graphs_possible(self, method, kwargs):
+        calc = self.calculator
+        if not (self.use_cuda_graphs and self._fast_path() and _dist() is None):
+            return False
+        if type(calc) is not CalculatorTorch or calc.model.device.type != "cuda":
+            return False  # the per-species calculator sizes its index sets on the host (not capturable)
+        if self.optimizer_state_path is not None or method not in ("Adam", "SGD"):
+            return False
+        if kwargs.get("weight_decay") or kwargs.get("amsgrad") or kwargs.get("momentum") or kwargs.get("fused"):
+            return False  # the state-initialising dummy step below must leave the parameters untouched
+        return True
+
+    def _prepare_graphs(self, method, kwargs):
+        """Rebuild the optimizer in its capturable form, give every parameter a static gradient,
+        run one eager forward/backward (library handles, autograd threads) and initialise the
+        optimizer state without moving the parameters.  Returns False (eager training) on failure."""
+        calc = self.calculator
+        params = [p for p in calc.model.parameters() if p.requires_grad]
+        dev = calc.model.device
+        try:
+            if method == "Adam":
+                self.optimizer = torch.optim.Adam(calc.model.parameters(), capturable=True, **kwargs)
+            self._weights_on_device()
+            n = len(calc.fingerprints_dataset)
+            bs = self.batch_size
+            fp = calc.fingerprints_dataset.fp
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for p in params:
+                    p.grad = torch.zeros_like(p)
+                loss = self._get_loss_batch(fp[0:min(bs, n)])
+                loss.backward()
+                for p in params:
+                    p.grad.zero_()
+                before = [p.detach().clone() for p in params]
+                self.optimizer.step()  # zero gradients: creates the state, moves nothing
+                for group in self.optimizer.param_groups:
+                    for p in group["params"]:
+                        st = self.optimizer.state.get(p, {})
+                        if torch.is_tensor(st.get("step")):
+                            st["step"].zero_()
+                same = all(torch.equal(a, p.detach()) for a, p in zip(before, params))
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            if not same:
+                raise RuntimeError("state-initialising step moved the parameters")
+            self._graphs = {}
+            self._graph_pool = torch.cuda.graph_pool_handle()
+            self._graph_acc = torch.zeros((), dtype=torch.float64, device=dev)
+            return True
+        except Exception as e:  # fall back to eager stepping; nothing has been updated
+            print(f"kliff_b200: CUDA-graph training disabled ({type(e).__name__}: {e})")
+            self.optimizer = getattr(torch.optim, method)(calc.model.parameters(), **kwargs)
+            for p in params:
+                p.grad = None
+            return False
+
+    def _graph_for(self, lo, hi, train):
+        key = (lo, hi, train)
+        g = self._graphs.get(key)
+        if g is None:
+            batch = self.calculator.fingerprints_dataset.fp[lo:hi]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._graph_pool):
+                with torch.enable_grad():
+                    if train:
+                        self.optimizer.zero_grad(set_to_none=False)
+                    loss = self._get_loss_batch(batch)
+                    if train:
+                        loss.backward()
+                        self.optimizer.step()
+                self._graph_acc.add_(loss.detach().to(torch.float64))
+            self._graphs[key] = g
+        return g
+
+    def _graphed_pass(self, train):
+        """One pass over the data set, one graph replay per batch; the epoch loss is accumulated on
+        the device and read once."""
+        n = len(self.calculator.fingerprints_dataset)
+        bs = self.batch_size
+        self._graph_acc.zero_()
+        for lo in range(0, n, bs):
+            self._graph_for(lo, min(lo + bs, n), train).replay()
+        return float(self._graph_acc)
+
     def _get_loss_epoch(self, loader):
+        if self._graph_acc is not None and self._graphs_live():
+            return self._graphed_pass(train=False)
         total = 0.0
         with torch.enable_grad():
             for batch in self._batches(loader):
                 loss = self._get_loss_batch(batch)
                 total += float(self._sync_loss(loss.detach()))
         return total
+
+    def _graphs_live(self):
+        return self._graph_pool is not None and self.use_cuda_graphs
 
     # ------------------------------------------------------------------ data-parallel plumbing
     def _sync_gradients(self, loss):
