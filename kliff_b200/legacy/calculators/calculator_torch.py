@@ -28,6 +28,19 @@ class CalculatorTorchError(Exception):
         self.msg = msg
 
 
+def _dist_active():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def _rank_suffix(filename, rank):
+    """fingerprints.pkl -> fingerprints.rank3.pkl (ranks of one node share the working directory)."""
+    path = to_path(filename)
+    return path.with_name(f"{path.stem}.rank{rank}{path.suffix}")
+
+
 def _get_device(gpu):
     """calculator_torch.py:582-594, minus the CPU branch."""
     if gpu is None or isinstance(gpu, bool):
@@ -65,11 +78,17 @@ class CalculatorTorch:
         self.results = dict([(i, None) for i in self.implemented_property])
         self._packed = None
         self._ref = None
+        self._shard = None
 
     # ------------------------------------------------------------------ create (:41-126)
     def create(self, configs, use_energy=True, use_forces=True, use_stress=False,
                fingerprints_filename="fingerprints.pkl", fingerprints_mean_stdev_filename=None,
-               reuse=False, use_welford_method=False, nprocs=1):
+               reuse=False, use_welford_method=False, nprocs=1, shard_configs=None):
+        """`shard_configs` (default: on whenever torch.distributed runs with more than one rank and
+        fingerprints are generated, not reused): rank r generates and keeps only configurations
+        r, r + world, r + 2 world, ... — the multi-GPU form of the reference's `parmap1` over
+        configurations (descriptor.py:234-236).  Mean / stdev are all-reduced, so every rank
+        normalises with the global statistics; `Loss` then takes each rank's members of every batch."""
         self.configs = configs
         self.use_energy = use_energy
         self.use_forces = use_forces
@@ -77,6 +96,17 @@ class CalculatorTorch:
         if not isinstance(configs, (list, tuple)):
             configs = [configs]
         desc = self.model.descriptor
+        self._shard = None
+        dist = _dist_active()
+        if dist is not None and not reuse and (shard_configs is None or shard_configs):
+            r, w = dist.get_rank(), dist.get_world_size()
+            self._shard = (r, w, len(configs))
+            configs = list(configs[r::w])
+            fingerprints_filename = _rank_suffix(fingerprints_filename, r)
+            if fingerprints_mean_stdev_filename is None:
+                fingerprints_mean_stdev_filename = "fingerprints_mean_and_stdev.pkl"
+            if r != 0:  # rank 0 writes the file the user asked for; the others keep private copies
+                fingerprints_mean_stdev_filename = _rank_suffix(fingerprints_mean_stdev_filename, r)
         if reuse:
             self.fingerprints_path = to_path(fingerprints_filename)
             if not self.fingerprints_path.exists():
@@ -94,7 +124,8 @@ class CalculatorTorch:
         else:
             self.fingerprints_path = desc.generate_fingerprints(
                 configs, use_forces, use_stress, fingerprints_filename,
-                fingerprints_mean_stdev_filename, use_welford_method, nprocs)
+                fingerprints_mean_stdev_filename, use_welford_method, nprocs,
+                **({"reduce_over": dist} if self._shard is not None else {}))
             self._packed = desc.packed_fingerprints
         self.fingerprints_dataset = FingerprintsDataset(self.fingerprints_path)
         if self._packed is None:
@@ -128,7 +159,7 @@ class CalculatorTorch:
         try:
             e = np.array([float(s["energy"]) for s in fp]) if self.use_energy else np.zeros(len(fp))
             f = (np.concatenate([np.asarray(s["forces"], np.float64).reshape(-1) for s in fp])
-                 if self.use_forces else np.zeros(0))
+                 if (self.use_forces and len(fp)) else np.zeros(0))
         except Exception:
             return
         self._ref = dict(energy=torch.as_tensor(e, device=dev).to(dt),

@@ -52,8 +52,10 @@ class Descriptor:
     def generate_fingerprints(self, configs, fit_forces=False, fit_stress=False,
                               fingerprints_filename="fingerprints.pkl",
                               fingerprints_mean_stdev_filename=None, use_welford_method=False,
-                              nprocs=1):
-        """`nprocs` is accepted for interface compatibility; the work is one GPU pass.
+                              nprocs=1, reduce_over=None):
+        """`reduce_over`: a torch.distributed module when `configs` is this rank's share of a
+        larger set — mean and stdev are then the statistics of the whole set (two all-reduces).
+        `nprocs` is accepted for interface compatibility; the work is one GPU pass.
         `use_welford_method` selects the same statistics computed in a streaming fashion in the
         reference (descriptor.py:243-282); both give the population mean/stdev, so it is a no-op."""
         if fit_stress and self.fingerprints_format != "dense":
@@ -67,8 +69,17 @@ class Descriptor:
         has_mean_stdev = self.mean is not None and self.stdev is not None
         if self.normalize and not has_mean_stdev:
             z = packed.zeta
-            mean = z.mean(dim=0)
-            stdev = torch.sqrt(((z - mean) ** 2).mean(dim=0))  # np.std, ddof = 0
+            if reduce_over is None:
+                mean = z.mean(dim=0)
+                stdev = torch.sqrt(((z - mean) ** 2).mean(dim=0))  # np.std, ddof = 0
+            else:
+                # same two-pass definition over all ranks' atoms: sum -> mean, then sum of squares
+                first = torch.cat([z.sum(dim=0), torch.tensor([float(z.shape[0])], dtype=z.dtype, device=z.device)])
+                reduce_over.all_reduce(first, op=reduce_over.ReduceOp.SUM)
+                mean = first[:-1] / first[-1]
+                second = ((z - mean) ** 2).sum(dim=0)
+                reduce_over.all_reduce(second, op=reduce_over.ReduceOp.SUM)
+                stdev = torch.sqrt(second / first[-1])
             self.mean = mean.cpu().numpy()
             self.stdev = stdev.cpu().numpy()
             if fingerprints_mean_stdev_filename is None:

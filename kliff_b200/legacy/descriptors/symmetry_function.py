@@ -113,7 +113,12 @@ class SymmetryFunction(Descriptor):
         device = device if device is not None else default_device()
         if not isinstance(configs, (list, tuple)):
             configs = [configs]
-        if configs and max(c.get_num_atoms() for c in configs) <= _BATCH_MAX_ATOMS:
+        if len(configs) == 0:  # a rank whose share of a sharded data set is empty
+            packed = PackedFingerprints(len(self), device)
+            packed.zeta = torch.zeros((0, len(self)), dtype=torch.float64, device=device)
+            packed.host_ready = None
+            return packed
+        if max(c.get_num_atoms() for c in configs) <= _BATCH_MAX_ATOMS:
             # many small cells: one CTA per configuration, 2 synchronisations for the whole list
             try:
                 packed = PackedFingerprints.from_configs(len(self), device, configs, self.species_code,

@@ -67,6 +67,11 @@ def _check_residual_data(data, default):
     return default
 
 
+class _Share(list):
+    """This rank's members of one global batch (sharded fingerprints); `nglobal` = size of the batch."""
+    nglobal = 0
+
+
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -170,10 +175,24 @@ class LossNeuralNetworkModel:
     def _batches(self, loader):
         """Batches of samples.  On the vectorised route the DataLoader's per-sample collate
         (numpy -> tensor for every value) is skipped: only configuration indices are needed."""
+        shard = getattr(self.calculator, "_shard", None)
+        if shard is not None and not self._fast_path():
+            raise LossError("fingerprints sharded over ranks need the default residual function; call "
+                            "`calc.create(..., shard_configs=False)` to keep every configuration on every rank")
         if self._fast_path():
-            n = len(self.calculator.fingerprints_dataset)
             bs = self.batch_size if getattr(self, "batch_size", None) else loader.batch_size
             fp = self.calculator.fingerprints_dataset.fp
+            if shard is not None:
+                # global batch [lo, hi) -> the local configurations r, r + w, ... that fall inside it:
+                # positions ceil((lo - r) / w) .. ceil((hi - r) / w) of the local list (a contiguous run)
+                r, w, n = shard
+                for lo in range(0, n, bs):
+                    hi = min(lo + bs, n)
+                    share = _Share(fp[max(0, -((r - lo) // w)):max(0, -((r - hi) // w))])
+                    share.nglobal = hi - lo
+                    yield share
+                return
+            n = len(self.calculator.fingerprints_dataset)
             for lo in range(0, n, bs):
                 yield fp[lo:min(lo + bs, n)]
         else:
@@ -222,7 +241,10 @@ class LossNeuralNetworkModel:
                     for p in group["params"]:
                         st = self.optimizer.state.get(p, {})
                         if torch.is_tensor(st.get("step")):
-                            st["step"].zero_()
+                            # float64 step counter: the bias corrections 1 - beta^t are then evaluated in
+                            # double precision like the eager optimizer's Python floats (a float32
+                            # counter moves an fp64 trajectory by 3e-7)
+                            st["step"] = torch.zeros((), dtype=torch.float64, device=dev)
                 same = all(torch.equal(a, p.detach()) for a, p in zip(before, params))
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
@@ -318,8 +340,11 @@ class LossNeuralNetworkModel:
                 and getattr(calc, "_ref", None) is not None and calc.use_energy and not calc.use_stress)
 
     def _get_loss_batch(self, batch, normalize=True):
-        nglobal = len(batch)
-        batch = self._my_share(batch)
+        if isinstance(batch, _Share):   # sharded fingerprints: already this rank's members
+            nglobal = batch.nglobal
+        else:
+            nglobal = len(batch)
+            batch = self._my_share(batch)
         if len(batch) == 0:
             params = list(self.calculator.model.parameters())
             loss = sum((p * 0.0).sum() for p in params)

@@ -73,14 +73,16 @@ def main():
     every = configs_from_npz("si_varying_alat.npz", weight=Weight(forces_weight=0.3), limit=60)
     confs = [every[i] for i in range(60) if every[i].get_num_atoms() == 64][:24]
 
-    def train(distributed):
+    def train(distributed, shard=True, batch_size=8):
         d = SymmetryFunction({"Si-Si": 5.0}, "cos", "set51", normalize=True, dtype=np.float64)
         m = NeuralNetwork(d)
         m.add_layers(nn.Linear(51, 10), nn.Tanh(), nn.Linear(10, 10), nn.Tanh(), nn.Linear(10, 1))
         calc = CalculatorTorch(m)
         tmp = tempfile.mkdtemp()
         calc.create(confs, fingerprints_filename=os.path.join(tmp, f"fp{rank}.pkl"),
-                    fingerprints_mean_stdev_filename=os.path.join(tmp, f"ms{rank}.pkl"))
+                    fingerprints_mean_stdev_filename=os.path.join(tmp, f"ms{rank}.pkl"),
+                    shard_configs=bool(distributed and shard))
+        held = len(calc.fingerprints_dataset)
         m.set_save_metadata(prefix=os.path.join(tmp, "model"), start=1000, frequency=1000)
         loss = Loss(calc)
         if not distributed:
@@ -88,19 +90,27 @@ def main():
             saved = L._dist
             L._dist = lambda: None
             try:
-                loss.minimize(method="Adam", num_epochs=3, batch_size=8, lr=0.01)
+                loss.minimize(method="Adam", num_epochs=3, batch_size=batch_size, lr=0.01)
             finally:
                 L._dist = saved
         else:
-            loss.minimize(method="Adam", num_epochs=3, batch_size=8, lr=0.01)
-        return np.array(loss.epoch_losses)
+            loss.minimize(method="Adam", num_epochs=3, batch_size=batch_size, lr=0.01)
+        return np.array(loss.epoch_losses), held
 
-    single = train(False)
-    multi = train(True)
+    single, _ = train(False)
+    multi, held = train(True)                      # fingerprints sharded over the ranks (default)
     out["dp_loss_relerr"] = float(np.max(np.abs(multi / single - 1)))
     out["dp_losses"] = multi.tolist()
+    out["dp_configs_held_by_rank0"] = held          # 24 / world
+    single5, _ = train(False, batch_size=5)         # batches that do not divide evenly over the ranks
+    multi5, _ = train(True, batch_size=5)
+    out["dp_loss_relerr_batch5"] = float(np.max(np.abs(multi5 / single5 - 1)))
+    replicated, held_all = train(True, shard=False)  # every rank keeps every configuration
+    out["dp_loss_relerr_replicated"] = float(np.max(np.abs(replicated / single - 1)))
+    out["dp_configs_held_replicated"] = held_all
     ok = (out["slab_zeta_relerr"] <= 1e-10 and out["slab_force_relerr"] <= 1e-10
-          and out["dp_loss_relerr"] <= 1e-9)
+          and out["dp_loss_relerr"] <= 1e-9 and out["dp_loss_relerr_batch5"] <= 1e-9
+          and out["dp_loss_relerr_replicated"] <= 1e-9 and held == len(confs[rank::world]) and held_all == 24)
     out["ok"] = bool(ok)
     if rank == 0:
         print(json.dumps(out))
