@@ -135,3 +135,29 @@ def test_runs_helper_and_share():
     from kliff_b200.legacy.calculators.calculator_torch import _runs
     assert _runs([0, 1, 2, 5, 6, 9]) == [(0, 3, 0), (5, 7, 3), (9, 10, 5)]
     assert _runs([]) == []
+
+
+def test_sharded_batches_cover_every_configuration_once():
+    """Host logic of sharded fingerprints: rank r keeps configurations r, r + w, ...; for every global
+    batch the ranks' shares are disjoint, contiguous in the local lists, and together the batch."""
+    from kliff_b200.legacy.loss import LossNeuralNetworkModel, _Share
+
+    n, bs = 37, 10
+    for world in (1, 2, 3, 8):
+        seen = []
+        for rank in range(world):
+            local = [{"index": k, "global": g} for k, g in enumerate(range(rank, n, world))]
+            calc = _StubCalculator(_Model(), local)
+            calc._shard = (rank, world, n)
+            loss = LossNeuralNetworkModel.__new__(LossNeuralNetworkModel)
+            loss.calculator, loss.batch_size = calc, bs
+            loss._fast_path = lambda: True
+            shares = list(loss._batches(None))
+            assert len(shares) == (n + bs - 1) // bs          # every rank walks every global batch
+            for b, share in enumerate(shares):
+                assert isinstance(share, _Share) and share.nglobal == min(bs, n - b * bs)
+                assert all(b * bs <= s["global"] < b * bs + bs for s in share)
+                idx = [s["index"] for s in share]
+                assert idx == list(range(idx[0], idx[0] + len(idx))) if idx else True
+                seen += [s["global"] for s in share]
+        assert sorted(seen) == list(range(n))
