@@ -276,12 +276,14 @@ def run_slab_workload(args, rank, world, dev):
             "gpu_launches": int(launches)}))
 
 
-def train_epoch_probe(ncfg, dev):
+def train_epoch_probe(ncfg, dev, world=1):
     """Second half of BASELINE.json's metric ("train epoch time"): synthetic set of `ncfg` 64-atom
     diamond-Si configurations (2x2x2 cells, a ~ U(5.2, 5.7), jitter 0.1 A, seed = index; reference
     energies/forces = N(0,1) noise), set51, MLP 51-10-10-1, Adam lr 1e-3, batch 100, fp32 model as in
     the reference's tutorials.  Reports create() (descriptors + dG/dr + normalisation) and the time
-    of one optimisation pass over the set through Loss.minimize."""
+    of one optimisation pass over the set through Loss.minimize.  With world > 1 every rank calls
+    this: configurations are sharded round-robin over the ranks (create) and every batch is
+    evaluated data-parallel with a gradient all-reduce per step; times are the max over ranks."""
     import contextlib
     import io
     import tempfile
@@ -316,21 +318,33 @@ def train_epoch_probe(ncfg, dev):
     tmp = tempfile.mkdtemp()
     model.set_save_metadata(prefix=os.path.join(tmp, "m"), start=10 ** 9, frequency=10 ** 9)
     calc = CalculatorTorch(model)
-    torch.cuda.synchronize()
+
+    def fence():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def over_ranks(seconds):
+        t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t)
+
+    fence()
     t0 = time.time()
     calc.create(confs, fingerprints_filename=os.path.join(tmp, "fp.pkl"),
                 fingerprints_mean_stdev_filename=os.path.join(tmp, "ms.pkl"))
     torch.cuda.synchronize()
-    t_create = time.time() - t0
+    t_create = over_ranks(time.time() - t0)
     loss = Loss(calc)
     with contextlib.redirect_stdout(io.StringIO()):
         loss.minimize(method="Adam", num_epochs=1, batch_size=100, lr=1e-3)  # warm-up epoch (+ final pass)
-        torch.cuda.synchronize()
+        fence()
         t0 = time.time()
         # the reference tutorial's run: 10 optimisation epochs + the final loss pass (nn_Si.rst:171-184)
         loss.minimize(method="Adam", num_epochs=10, batch_size=100, lr=1e-3)
         torch.cuda.synchronize()
-        t_run = time.time() - t0
+        t_run = over_ranks(time.time() - t0)
         # steady state: passes over already-captured graphs (or eager steps when graphs are off)
         t0 = time.time()
         for _ in range(3):
@@ -342,7 +356,8 @@ def train_epoch_probe(ncfg, dev):
             loss._graphed_pass(train=True) if loss._graphs_live() else None
         torch.cuda.synchronize()
         t_train = (time.time() - t0) / 3.0
-    return {"configs": ncfg, "atoms": 64 * ncfg, "create_s": t_create,
+    return {"configs": ncfg, "atoms": 64 * ncfg, "n_gpus": world,
+            "configs_on_rank0": len(calc.fingerprints_dataset), "create_s": t_create,
             "epoch_s": t_run / 11.0, "steps_per_epoch": (ncfg + 99) // 100,
             "cuda_graphs": bool(loss._graphs_live()), "loss_pass_replay_s": t_eval if loss._graphs_live() else None,
             "train_pass_replay_s": t_train if loss._graphs_live() else None,
@@ -398,7 +413,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that fails leaves the others in a collective: bound that wait to minutes, not the default
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     ops.device_info()  # raises unless sm_100
     if args.workload == "slab":
         run_slab_workload(args, rank, world, dev)
@@ -510,6 +527,14 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(e2e_s)
 
+    # second half of the metric: the training-epoch probe (all ranks: sharded create + data-parallel steps)
+    train_epoch = None
+    if args.epoch_configs > 0:
+        try:
+            train_epoch = train_epoch_probe(args.epoch_configs, dev, world)
+        except Exception as e:  # reported, never required (single-process case only: see NCCL timeout)
+            train_epoch = {"error": str(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -562,11 +587,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    if args.epoch_configs > 0 and world == 1:
-        try:
-            line["train_epoch"] = train_epoch_probe(args.epoch_configs, dev)
-        except Exception as e:  # reported, never required
-            line["train_epoch"] = {"error": str(e)}
+    if train_epoch is not None:
+        line["train_epoch"] = train_epoch
     if cpu_base is not None:
         try:
             if isinstance(cpu_base, Exception):
