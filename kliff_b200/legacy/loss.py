@@ -202,7 +202,7 @@ class LossNeuralNetworkModel:
     # ------------------------------------------------------------------ CUDA-graph stepping
     def _graphs_possible(self, method, kwargs):
         calc = self.calculator
-        if not (self.use_cuda_graphs and self._fast_path() and _dist() is None):
+        if not (self.use_cuda_graphs and self._fast_path()):
             return False
         if type(calc) is not CalculatorTorch or calc.model.device.type != "cuda":
             return False  # the per-species calculator sizes its index sets on the host (not capturable)
@@ -223,16 +223,14 @@ class LossNeuralNetworkModel:
             if method == "Adam":
                 self.optimizer = torch.optim.Adam(calc.model.parameters(), capturable=True, **kwargs)
             self._weights_on_device()
-            n = len(calc.fingerprints_dataset)
-            bs = self.batch_size
-            fp = calc.fingerprints_dataset.fp
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for p in params:
                     p.grad = torch.zeros_like(p)
-                loss = self._get_loss_batch(fp[0:min(bs, n)])
+                loss = self._get_loss_batch(next(iter(self._batches(None))))
                 loss.backward()
+                self._sync_gradients(loss)  # also brings up the NCCL communicator before any capture
                 for p in params:
                     p.grad.zero_()
                 before = [p.detach().clone() for p in params]
@@ -261,11 +259,10 @@ class LossNeuralNetworkModel:
                 p.grad = None
             return False
 
-    def _graph_for(self, lo, hi, train):
-        key = (lo, hi, train)
+    def _graph_for(self, b, batch, train):
+        key = (b, train)
         g = self._graphs.get(key)
         if g is None:
-            batch = self.calculator.fingerprints_dataset.fp[lo:hi]
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self._graph_pool):
                 with torch.enable_grad():
@@ -274,19 +271,20 @@ class LossNeuralNetworkModel:
                     loss = self._get_loss_batch(batch)
                     if train:
                         loss.backward()
+                        total = self._sync_gradients(loss)  # gradient + loss all-reduce (captured too)
                         self.optimizer.step()
-                self._graph_acc.add_(loss.detach().to(torch.float64))
+                    else:
+                        total = self._sync_loss(loss.detach())
+                self._graph_acc.add_(total.detach().to(torch.float64))
             self._graphs[key] = g
         return g
 
     def _graphed_pass(self, train):
-        """One pass over the data set, one graph replay per batch; the epoch loss is accumulated on
-        the device and read once."""
-        n = len(self.calculator.fingerprints_dataset)
-        bs = self.batch_size
+        """One pass over the data set, one graph replay per (global) batch; the epoch loss is
+        accumulated on the device and read once."""
         self._graph_acc.zero_()
-        for lo in range(0, n, bs):
-            self._graph_for(lo, min(lo + bs, n), train).replay()
+        for b, batch in enumerate(self._batches(None)):
+            self._graph_for(b, batch, train).replay()
         return float(self._graph_acc)
 
     def _get_loss_epoch(self, loader):
