@@ -722,6 +722,11 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
   // chunk of atoms whose records are alive at the same time
   int chunk = 1 << 18;
   if (const char* c = getenv("KB_SPLIT_CHUNK")) { const int v = atoi(c); if (v >= 1024) chunk = v; }
+  {
+    // records of a chunk stay below ~6 GB of scratch whatever the record stride (82 KB at n = 64)
+    const long long cap = (6LL << 30) / L.bytes;
+    if (chunk > cap) chunk = (int) (cap < 8192 ? 8192 : cap);
+  }
   if (chunk > n_centers) chunk = n_centers;
   const int n_chunks = (n_centers + chunk - 1) / chunk;
   unsigned char* records = nullptr;

@@ -40,8 +40,10 @@ def main():
     print("device", torch.cuda.get_device_name(0), ops.device_info())
     print("fp64 peak TFLOP/s", ops.probe_fp64_peak())
     print("hbm copy GB/s", ops.probe_hbm_copy(1 << 30))
-    P = ops.build_params(get_set51(), np.array([[5.0]]))
+    two_species = os.environ.get("KB_SPECIES", "1") == "2"  # zinc-blende decoration, all cutoffs 5.0 (M1-SiC)
+    P = ops.build_params(get_set51(), np.full((2, 2), 5.0) if two_species else np.array([[5.0]]))
     mode = int(os.environ.get("KB_MODE", "0"))  # include/kliff_b200.h KB_SYMFUN_*
+    dz_dtype = torch.float32 if os.environ.get("KB_DZ", "f64") == "f32" else torch.float64
     for nx in [int(a) for a in sys.argv[1:]] or [10, 30, 50]:
         cell, pos = diamond(nx)
         n = len(pos)
@@ -51,8 +53,11 @@ def main():
         allc = torch.cat([coords, pc])
         t_nl, (counts, offsets, indices, maxn) = timed(lambda: ops.build_neighbors(allc, n, 5.0))
         species = torch.zeros(allc.shape[0], dtype=torch.int32, device=dev)
+        if two_species:  # basis atoms 0-3 Si, 4-7 C; images inherit their owner's species
+            own = torch.cat([torch.arange(n, device=dev), pi.long()])
+            species = ((own % 8) >= 4).to(torch.int32)
         dz_ptr, total = ops.block_offsets(n, None, offsets, 51)
-        dz = torch.empty(total, dtype=torch.float64, device=dev)
+        dz = torch.empty(total, dtype=dz_dtype, device=dev)
         t_sf, (zeta, _, _) = timed(lambda: ops.symfun_forward(P, allc, species, offsets, indices, maxn,
                                                               n_centers=n, dz_ptr=dz_ptr, dz=dz, mode=mode))
         t_z, _ = timed(lambda: ops.symfun_forward(P, allc, species, offsets, indices, maxn,
@@ -66,8 +71,10 @@ def main():
                               ms_pad=t_pad, ms_nl=t_nl, ms_symfun_grad=t_sf, ms_symfun_zeta=t_z,
                               ms_scatter_fwd=t_f, ms_scatter_bwd=t_b,
                               atoms_per_s_symfun=n / t_sf * 1e3,
-                              dz_GB=total * 8 / 1e9, symfun_GBps=total * 8 / t_sf / 1e6,
-                              scatter_fwd_GBps=total * 8 / t_f / 1e6, scatter_bwd_GBps=total * 8 / t_b / 1e6)))
+                              dz_GB=total * dz.element_size() / 1e9, symfun_GBps=total * dz.element_size() / t_sf / 1e6,
+                              scatter_fwd_GBps=total * dz.element_size() / t_f / 1e6,
+                              scatter_bwd_GBps=total * dz.element_size() / t_b / 1e6,
+                              species=2 if two_species else 1, dz_dtype=str(dz_dtype))))
 
 
 if __name__ == "__main__":
