@@ -280,7 +280,7 @@ symfun_tiled_kernel(const __grid_constant__ kb_symfun_params P, const TiledArgs 
         const int j = __ffsll((long long) mask) - 1;
         mask &= mask - 1;
         const int rec = prow[j];
-        const double rij = Rr[j], rij2 = R2[j], irij = IR[j], fij = FC[j];
+        const double rij2 = R2[j], irij = IR[j], fij = FC[j];
         const double rjk = RR[rec], fjk = is5 ? 1.0 : RFC[rec], dfjk = is5 ? 0.0 : RDFC[rec];
         const double sg = (k > j) ? 1.0 : -1.0;  // record orientation is low slot -> high slot
         const double ujkx = sg * RU[rec], ujky = sg * RU[RC + rec], ujkz = sg * RU[2 * RC + rec];

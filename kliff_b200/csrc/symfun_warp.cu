@@ -79,7 +79,7 @@ struct WarpArgs
 
 __host__ __device__ inline size_t warp_smem_bytes(const kb_symfun_params& P, int NP, int RC)
 {
-  const int NG = P.n_groups, NT = P.n_two;
+  const int NT = P.n_two;
   size_t d = (size_t) 3 * NP + (size_t) NP * 8 + (size_t) RC * 4 + SC_DOUBLES + 4 * (size_t) NT
              + (size_t) P.n_species * P.n_species + 64;
   size_t bytes = d * 8 + (size_t) NP * 8;        // + adjacency masks
