@@ -427,21 +427,26 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
   int tt_next = 0;
   if (lane == 0) tt_next = A.lo + atomicAdd(A.work, 1);
   tt_next = __shfl_sync(FULL, tt_next, 0);
+  int4 hdr_next = make_int4(-1, 0, 0, 0);
+  if (tt_next < A.hi)
+    hdr_next = __ldcg(reinterpret_cast<const int4*>(A.records + (size_t) (tt_next - A.lo) * L.bytes));
   for (;;)
   {
     const int tt = tt_next;
     if (tt >= A.hi) break;
+    const int4 hdr = hdr_next;
     if (lane == 0) tt_next = A.lo + atomicAdd(A.work, 1);
     tt_next = __shfl_sync(FULL, tt_next, 0);
     const int t = A.subset ? A.subset[tt] : tt;
     const unsigned char* rec = A.records + (size_t) (tt - A.lo) * L.bytes;
-    const int4 hdr = __ldcg(reinterpret_cast<const int4*>(rec));
     const int n = hdr.x, nrec = hdr.y;
     if (tt_next < A.hi)
     {
-      // the lists / tables part of the next record (its pair records follow at L.rk; their count is
-      // not known yet, fetch the typical half of the capacity)
+      // next atom: its header now (consumed one atom later, so the load latency is never waited for)
+      // and its lists / tables into L2 (the pair records follow at L.rk; their count is not known
+      // yet, fetch the typical half of the capacity)
       const unsigned char* nx = A.records + (size_t) (tt_next - A.lo) * L.bytes;
+      hdr_next = __ldcg(reinterpret_cast<const int4*>(nx));
       const int lines = (L.rk + 16 * A.RC + 127) >> 7;
       for (int q = lane; q < lines; q += 32)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + ((size_t) q << 7)));
