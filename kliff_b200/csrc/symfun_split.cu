@@ -759,9 +759,10 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
     A.ang_lo = contiguous ? lo : 0;
     A.ang_hi = contiguous ? hi : 0;
     // Off by default: it removes the stage's excess DRAM traffic (82.2 -> 60.3 KB per atom at 1M atoms,
-    // profiles/r01_ncu_symfun_split_1M_traffic.txt) but costs 2.8 % of sweep time, because the extra
-    // 30 KB per atom go through the L1/shared data pipe, which is this kernel's tightest unit while
-    // DRAM is only 29 % busy.  KB_PREZERO=1 switches it on.
+    // profiles/r01_ncu_symfun_split_1M_traffic.txt) but costs 2.8 % of sweep time while DRAM is only
+    // 29 % busy.  The cost is not the store path (the same zeros sent as cp.async.bulk copies measure
+    // identically); the row pieces themselves get slower once they land on resident dirty lines.
+    // KB_PREZERO=1 switches it on.
     const char* pz = getenv("KB_PREZERO");
     if (!(pz && pz[0] == '1')) A.ang_lo = A.ang_hi = 0;
   }
