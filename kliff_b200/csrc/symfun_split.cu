@@ -128,7 +128,34 @@ __device__ __forceinline__ int build_lists(int n, int NP, int S, M act, const do
   {
     const int j = j0 + lane;
     M mask = 0;
-    if (j < n)
+    if (sizeof(M) == 4)
+    {
+      // n <= 32, one row per lane: every unordered pair once.  In round m lane j tests the pair
+      // (j, j + m mod n) and hands the verdict to lane j + m through a shuffle, so n/2 rounds cover
+      // the n(n-1)/2 pairs (the predicate is symmetric bit for bit: (xk - xj)^2 == (xj - xk)^2).
+      const bool rowok = j < n;
+      const int jc = rowok ? j : 0;
+      const double xj = XYZ[jc], yj = XYZ[NP + jc], zj = XYZ[2 * NP + jc];
+      const int prow = SPC[jc] * S;
+      for (int m = 1; m <= n / 2; m++)
+      {
+        int k = jc + m;
+        k = k >= n ? k - n : k;
+        const double r2 = xnorm2(xsub(XYZ[k], xj), xsub(XYZ[NP + k], yj), xsub(XYZ[2 * NP + k], zj));
+        const int pr = prow + SPC[k];
+        bool hit = r2 < R2LO[pr];
+        if (!hit && r2 <= R2HI[pr]) hit = !(sqrt(r2) > rcut[pr]);
+        hit = hit && rowok;
+        int src = lane - m;               // the lane whose partner in this round is this lane
+        src = src < 0 ? src + n : src;
+        const bool hin = __shfl_sync(FULL, (int) hit, src & 31) != 0;
+        mask |= (M) hit << k;
+        if (rowok) mask |= (M) hin << src;
+      }
+      mask &= ~(one << jc) & act;
+      if (!rowok || !((act >> jc) & one)) mask = 0;
+    }
+    else if (j < n)
     {
       const double xj = XYZ[j], yj = XYZ[NP + j], zj = XYZ[2 * NP + j];
       const int prow = SPC[j] * S;
