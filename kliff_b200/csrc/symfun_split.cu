@@ -385,13 +385,30 @@ symfun_prep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A
     }
 
     // ---- phase S: slots ordered by adjacency degree (descending, index as tie-break) ---------
-    for (int k = lane; k < n; k += 32)
+    if (n <= 32)
     {
-      const int dk = DEG[k];
-      int rank = 0;
-      for (int m = 0; m < n; m++) rank += (DEG[m] > dk) || (DEG[m] == dk && m < k);
-      KORD[rank] = (unsigned char) k;
+      // one slot per lane, degrees < 32: bit-serial ballots from the top bit down leave in `tied` the
+      // lanes with the same degree and count in `above` the slots with a larger one
+      const int dk = lane < n ? DEG[lane] : 0;
+      unsigned tied = n == 32 ? FULL : ((1u << n) - 1u);
+      int above = 0;
+#pragma unroll
+      for (int b = 4; b >= 0; b--)
+      {
+        const unsigned bal = __ballot_sync(FULL, (dk >> b) & 1);
+        if ((dk >> b) & 1) tied &= bal;
+        else { above += __popc(tied & bal); tied &= ~bal; }
+      }
+      if (lane < n) KORD[above + __popc(tied & ((1u << lane) - 1u))] = (unsigned char) lane;
     }
+    else
+      for (int k = lane; k < n; k += 32)
+      {
+        const int dk = DEG[k];
+        int rank = 0;
+        for (int m = 0; m < n; m++) rank += (DEG[m] > dk) || (DEG[m] == dk && m < k);
+        KORD[rank] = (unsigned char) k;
+      }
     __syncwarp();
 
     // ---- record: lists, order, header ----------------------------------------------------------
