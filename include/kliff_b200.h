@@ -177,6 +177,7 @@ void kb_batch_destroy(kb_batch_plan* plan, void* stream);
 #define KB_SYMFUN_TILED 2       /* CTA-per-atom shared-memory kernel: n <= 64, any families */
 #define KB_SYMFUN_WARP 3        /* warp-per-atom kernel: n <= 64, g1-g4 with zeta in {1,2,4,16}, lambda = +-1 */
 #define KB_SYMFUN_SPLIT 4       /* same domain as WARP, two launches: table kernel + triple-sweep kernel (AUTO's first choice) */
+#define KB_SYMFUN_WS 5          /* same domain, one warp-specialised kernel: table warps feed sweep warps inside each CTA */
 
 int kb_symfun_block_offsets(int32_t n_centers, const int32_t* d_centers,
                             const int64_t* d_nl_offsets, int32_t n_desc, int64_t* d_dz_ptr,
@@ -226,9 +227,9 @@ int kb_probe_hbm_copy(size_t bytes, double* h_gbs, void* stream);
 /* Number of kernels this library has launched in this process (reset != 0 zeroes it). */
 int64_t kb_launch_count(int32_t reset);
 /* Per-kernel device times of the descriptor stage, measured with CUDA events on the launching
- * stream.  Returns in h_ms[3] / h_launches[3] (either may be NULL) the summed duration and number
+ * stream.  Returns in h_ms[4] / h_launches[4] (either may be NULL) the summed duration and number
  * of launches recorded since the previous call, by kernel: [0] symfun_prep_kernel, [1]
- * symfun_sweep_kernel, [2] fused symfun_warp_kernel; then switches recording on (enable != 0) or
+ * symfun_sweep_kernel, [2] fused symfun_warp_kernel, [3] symfun_ws_kernel; then switches recording on (enable != 0) or
  * off.  Off by default: no events are created unless a caller (bench.py) asks. */
 int kb_kernel_timing(int32_t enable, double* h_ms, int32_t* h_launches);
 

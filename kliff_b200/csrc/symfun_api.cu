@@ -24,6 +24,12 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
                            void* d_dz, int dz_dtype, const int64_t* d_dz_ptr, int32_t* d_overflow,
                            bool* launched, bool* may_overflow, cudaStream_t st);
 
+int kb_symfun_ws_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
+                        const int32_t* d_subset, const double* d_coords, const int32_t* d_species,
+                        const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn, double* d_zeta,
+                        void* d_dz, int dz_dtype, const int64_t* d_dz_ptr, int32_t* d_overflow,
+                        bool* launched, bool* may_overflow, cudaStream_t st);
+
 namespace {
 
 __global__ void block_size_kernel(int n_centers, const int32_t* __restrict__ centers,
@@ -109,7 +115,7 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
   // ---- preferred: warp-per-atom kernels (g4 sets with canonical exponents, n <= 64): the two-stage
   //      form first (table kernel + triple-sweep kernel), the fused kernel on request and for the
   //      atoms the first pass declines
-  if (mode == KB_SYMFUN_AUTO || mode == KB_SYMFUN_WARP || mode == KB_SYMFUN_SPLIT)
+  if (mode == KB_SYMFUN_AUTO || mode == KB_SYMFUN_WARP || mode == KB_SYMFUN_SPLIT || mode == KB_SYMFUN_WS)
   {
     int32_t* ov = nullptr;
     KB_CUDA(cudaMallocAsync((void**) &ov, sizeof(int32_t) * ((size_t) n_centers + 2), st));
@@ -119,6 +125,10 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
       rc = kb_symfun_warp_launch(P, n_centers, d_centers, nullptr, d_coords, d_species, d_nl_offsets,
                                  d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov, 0, &launched,
                                  &may_overflow, st);
+    else if (mode == KB_SYMFUN_WS)
+      rc = kb_symfun_ws_launch(P, n_centers, d_centers, nullptr, d_coords, d_species, d_nl_offsets,
+                               d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov, &launched,
+                               &may_overflow, st);
     else
       rc = kb_symfun_split_launch(P, n_centers, d_centers, nullptr, d_coords, d_species, d_nl_offsets,
                                   d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov, &launched,

@@ -25,7 +25,7 @@ def main():
         allc = torch.cat([coords, pc])
         counts, offsets, indices, maxn = ops.build_neighbors(allc, n, 5.0)
         species = torch.zeros(allc.shape[0], dtype=torch.int32, device=dev)
-        zeta, dz, dz_ptr = ops.symfun_forward(P, allc, species, offsets, indices, maxn, n_centers=n)
+        zeta, dz, dz_ptr = ops.symfun_forward(P, allc, species, offsets, indices, maxn, n_centers=n, mode=int(__import__("os").environ.get("KB_MODE", "0")))
         image = torch.cat([torch.arange(n, dtype=torch.int32, device=dev), pi])
         pack = dict(offsets=offsets, indices=indices, image=image, dz=dz, dz_ptr=dz_ptr, D=51, n_out=n)
         w = torch.randn(n, 51, dtype=torch.float64, device=dev)
