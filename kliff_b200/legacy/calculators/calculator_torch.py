@@ -127,7 +127,10 @@ class CalculatorTorch:
                 fingerprints_mean_stdev_filename, use_welford_method, nprocs,
                 **({"reduce_over": dist} if self._shard is not None else {}))
             self._packed = desc.packed_fingerprints
-        self.fingerprints_dataset = FingerprintsDataset(self.fingerprints_path)
+        examples = None if reuse else getattr(desc, "last_examples", None)
+        self.fingerprints_dataset = FingerprintsDataset(examples if examples is not None
+                                                        else self.fingerprints_path)
+        desc.last_examples = None
         if self._packed is None:
             self._packed = self._packed_from_samples(self.fingerprints_dataset.fp)
         self._upload_references()

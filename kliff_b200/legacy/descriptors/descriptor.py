@@ -95,7 +95,9 @@ class Descriptor:
             packed.zeta_normalized = packed.zeta
             packed.scale = None
         self.packed_fingerprints = packed
-        self._dump_fingerprints(configs, fingerprints_filename, packed, fit_forces, dense_stress)
+        # the examples just written, for callers that would otherwise read the file straight back
+        self.last_examples = self._dump_fingerprints(configs, fingerprints_filename, packed, fit_forces,
+                                                     dense_stress)
         return fingerprints_filename
 
     def _dump_fingerprints(self, configs, fname, packed, fit_forces, fit_stress):
@@ -106,6 +108,7 @@ class Descriptor:
             fname.unlink()
         zeta_all = packed.zeta_normalized.cpu().numpy()
         inv = packed.scale
+        examples = []
         with open(fname, "ab") as f:
             for i, conf in enumerate(configs):
                 lo, hi = packed.config_slice(i)
@@ -129,6 +132,8 @@ class Descriptor:
                     example["stress"] = np.asarray(conf.stress, self.dtype)
                     example["volume"] = np.asarray(conf.get_volume(), self.dtype)
                 pickle.dump(example, f)
+                examples.append(example)
+        return examples
 
     # ------------------------------------------------------------------ getters (descriptor.py:315-353)
     def get_size(self):

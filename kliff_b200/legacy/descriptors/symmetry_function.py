@@ -168,6 +168,7 @@ class SymmetryFunction(Descriptor):
         state = self.__dict__.copy()
         state["_params"] = None              # ctypes struct: rebuilt on load
         state["packed_fingerprints"] = None  # device memory does not pickle
+        state["last_examples"] = None
         return state
 
     def __setstate__(self, state):
