@@ -110,6 +110,9 @@ class Descriptor:
         inv = packed.scale
         examples = []
         with open(fname, "ab") as f:
+            # one Pickler for the whole stream, memo cleared per example: the file is the same sequence
+            # of independent pickles that repeated pickle.dump() calls write (load_fingerprints reads it)
+            pickler = pickle.Pickler(f, protocol=pickle.HIGHEST_PROTOCOL)
             for i, conf in enumerate(configs):
                 lo, hi = packed.config_slice(i)
                 zeta = np.asarray(zeta_all[lo:hi], self.dtype)
@@ -131,7 +134,8 @@ class Descriptor:
                     example["dzetadr_stress"] = np.asarray(stress.cpu().numpy(), self.dtype)
                     example["stress"] = np.asarray(conf.stress, self.dtype)
                     example["volume"] = np.asarray(conf.get_volume(), self.dtype)
-                pickle.dump(example, f)
+                pickler.dump(example)
+                pickler.clear_memo()
                 examples.append(example)
         return examples
 
