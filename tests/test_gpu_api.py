@@ -305,3 +305,46 @@ def test_new_api_descriptor_forward_backward():
     state = new(config, return_extended_state=True)
     assert state["n_atoms"] == 64 and state["descriptor"].shape == (64, 51)
     assert state["num_neigh"].shape == (64,) and state["neigh_list"].shape[0] == state["num_neigh"].sum()
+
+
+def test_calculator_stress_matches_strain_derivative(workdir):
+    """`use_stress=True` (calculator_torch.py:271-274 with dzetadr_stress of sym_fn.py:176-185):
+    the predicted stress is dE/d(strain)/V in Voigt order 11,22,33,23,31,12.  Checked against a
+    central finite difference of the model energy under a homogeneous strain of cell + coordinates."""
+    every = configs_from_npz("si_varying_alat.npz", limit=8)
+    base = every[7]
+    cell0, pos0 = np.asarray(base.cell, float), np.asarray(base.coords, float)
+
+    def conf_with(strain):
+        F = np.eye(3) + strain
+        return Configuration(cell=cell0 @ F.T, species=list(base.species), coords=pos0 @ F.T, PBC=[True] * 3,
+                             energy=0.0, forces=np.zeros_like(pos0), stress=[0.0] * 6)
+
+    desc = SymmetryFunction({"Si-Si": 5.0}, "cos", "set30", normalize=False, dtype=np.float64)
+    model = make_model(desc)
+    calc = CalculatorTorch(model)
+    voigt = [(0, 0), (1, 1), (2, 2), (1, 2), (2, 0), (0, 1)]
+    h = 1e-5
+    confs = [conf_with(np.zeros((3, 3)))]
+    for a, b in voigt:
+        for sgn in (+1, -1):
+            e = np.zeros((3, 3))
+            e[a, b] += 0.5 * sgn * h
+            e[b, a] += 0.5 * sgn * h
+            confs.append(conf_with(e))
+    calc.create(confs, use_energy=True, use_forces=True, use_stress=True,
+                fingerprints_filename="fp_stress.pkl")
+    torch.manual_seed(5)
+    for p in model.parameters():
+        p.data.normal_(0.0, 0.3)
+    out = calc.compute(next(iter(calc.get_compute_arguments(batch_size=len(confs)))))
+    energy = [float(e.detach()) for e in out["energy"]]
+    stress = out["stress"][0].detach().cpu().numpy()
+    vol = abs(np.linalg.det(cell0))
+    fd = np.array([(energy[1 + 2 * v] - energy[2 + 2 * v]) / (2.0 * h) / vol for v in range(6)])
+    assert np.allclose(stress, fd, rtol=2e-5, atol=2e-7 * np.abs(fd).max()), (stress, fd)
+    # forces of the same call are consistent with the packed route
+    packed = CalculatorTorch(model)
+    packed.create(confs[:1], fingerprints_filename="fp_stress2.pkl")
+    ref = packed.compute(next(iter(packed.get_compute_arguments(batch_size=1))))
+    assert torch.allclose(out["forces"][0].cpu(), ref["forces"][0].cpu(), rtol=1e-9, atol=1e-12)
