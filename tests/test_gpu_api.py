@@ -348,3 +348,7 @@ def test_calculator_stress_matches_strain_derivative(workdir):
     packed.create(confs[:1], fingerprints_filename="fp_stress2.pkl")
     ref = packed.compute(next(iter(packed.get_compute_arguments(batch_size=1))))
     assert torch.allclose(out["forces"][0].cpu(), ref["forces"][0].cpu(), rtol=1e-9, atol=1e-12)
+    # and the loss with a stress term runs through the per-configuration residual route (loss.py:879-920)
+    loss = Loss(calc)
+    loss.minimize(method="Adam", num_epochs=1, batch_size=5, lr=1e-3)
+    assert len(loss.epoch_losses) == 2 and all(np.isfinite(v) and v > 0 for v in loss.epoch_losses)
