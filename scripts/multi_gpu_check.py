@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from kliff_b200.dataset import Configuration
 from kliff_b200.dataset.weight import Weight
 from kliff_b200.legacy import nn
-from kliff_b200.legacy.calculators import CalculatorTorch
+from kliff_b200.legacy.calculators import CalculatorTorch, CalculatorTorchSeparateSpecies
 from kliff_b200.legacy.descriptors import SymmetryFunction
 from kliff_b200.legacy.loss import Loss
 from kliff_b200.models import NeuralNetwork
@@ -108,7 +108,41 @@ def main():
     replicated, held_all = train(True, shard=False)  # every rank keeps every configuration
     out["dp_loss_relerr_replicated"] = float(np.max(np.abs(replicated / single - 1)))
     out["dp_configs_held_replicated"] = held_all
+    # ---- 3. config 3: two-species SiC set, one MLP per species, configurations sharded over the ranks
+    sic = configs_from_npz("sic_training_set.npz", weight=Weight(forces_weight=0.3))
+
+    def train_sic(distributed):
+        d = SymmetryFunction({"Si-Si": 5.0, "C-C": 5.0, "Si-C": 5.0}, "cos", "set51", normalize=True, dtype=np.float64)
+        models = {}
+        tmp = tempfile.mkdtemp()
+        for name in ("Si", "C"):
+            m = NeuralNetwork(d)
+            m.add_layers(nn.Linear(51, 10), nn.Tanh(), nn.Linear(10, 10), nn.Tanh(), nn.Linear(10, 1))
+            m.set_save_metadata(prefix=os.path.join(tmp, "model_" + name), start=1000, frequency=1000)
+            models[name] = m
+        calc = CalculatorTorchSeparateSpecies(models)
+        calc.create(sic, fingerprints_filename=os.path.join(tmp, f"fp{rank}.pkl"),
+                    fingerprints_mean_stdev_filename=os.path.join(tmp, f"ms{rank}.pkl"),
+                    shard_configs=bool(distributed))
+        loss = Loss(calc)
+        if not distributed:
+            import kliff_b200.legacy.loss as L
+            saved = L._dist
+            L._dist = lambda: None
+            try:
+                loss.minimize(method="Adam", num_epochs=3, batch_size=4, lr=0.001)
+            finally:
+                L._dist = saved
+        else:
+            loss.minimize(method="Adam", num_epochs=3, batch_size=4, lr=0.001)
+        return np.array(loss.epoch_losses), len(calc.fingerprints_dataset)
+
+    sic_single, _ = train_sic(False)
+    sic_multi, sic_held = train_sic(True)
+    out["sic_dp_loss_relerr"] = float(np.max(np.abs(sic_multi / sic_single - 1)))
+    out["sic_configs_held_by_rank0"] = sic_held
     ok = (out["slab_zeta_relerr"] <= 1e-10 and out["slab_force_relerr"] <= 1e-10
+          and out["sic_dp_loss_relerr"] <= 1e-9
           and out["dp_loss_relerr"] <= 1e-9 and out["dp_loss_relerr_batch5"] <= 1e-9
           and out["dp_loss_relerr_replicated"] <= 1e-9 and held == len(confs[rank::world]) and held_all == 24)
     out["ok"] = bool(ok)
