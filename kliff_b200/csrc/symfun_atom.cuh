@@ -23,11 +23,12 @@ constexpr int SJ = 8, SR = 4;
 constexpr int PREP_WARPS = 4;
 
 // Register caps of the sweep kernel (one warp per CTA) and the resident warps per SM they allow.
-// The gradient variant wants ~248 registers (8 warps per SM).  Capping it lower buys residency
-// (200 -> 10 warps with 5 doubles spilled) but measures slower (7.7 -> 8.2 ms on 216k atoms): the
-// kernel is bound by the shared-memory data pipe and the FP64 pipe, not by latency.
+// The gradient variant compiles to 230 registers uncapped (8 warps per SM); 224 gives 9 warps with a
+// handful of spilled values outside the inner loop and measures 1.3 % faster (33.9 -> 33.5 ms at 1M
+// atoms).  Going further does not pay (200 registers / 10 warps: 7.7 -> 8.2 ms on 216k atoms): the
+// kernel is bound by the FP64 pipe and the shared-memory data pipe, not by latency.
 #ifndef KB_SWEEP_REGS
-#define KB_SWEEP_REGS 248
+#define KB_SWEEP_REGS 224
 #endif
 #ifndef KB_SWEEP_REGS_NOGRAD
 #define KB_SWEEP_REGS_NOGRAD 128

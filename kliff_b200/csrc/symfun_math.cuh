@@ -86,6 +86,9 @@ __device__ __forceinline__ double kb_exp_tab(double x, const double* __restrict_
   return p * ts;
 }
 
+// (A 16-entry table with a degree-6 polynomial makes the lookup conflict-free but measured the same:
+// 7.37 ms either way on 216 k atoms.)
+
 // sin(pi y), cos(pi y) for 0 <= y <= 1 (also fine slightly outside).
 __device__ __forceinline__ void kb_sincospi01(double y, double& s, double& c)
 {
