@@ -7,17 +7,18 @@
 // cycles, and with 242 registers per thread only 8 warps fit on an SM to hide that.  So the two
 // halves want opposite launch shapes, and here they get them:
 //
-//   symfun_prep_kernel   ~100 registers, 2.5-5 KB of shared memory per warp -> 5x the resident warps.
+//   symfun_prep_kernel   80 registers, 4.6 KB of shared memory per warp -> 24 resident warps per SM.
 //                        Per atom: phases A, D, B, C, S of symfun_warp.cu (same arithmetic, same
 //                        order), radial rows of dG/dr written to their final place, and the tables
 //                        the sweep needs packed into one "atom record" in global memory.
-//   symfun_sweep_kernel  persistent, 8+ warps per SM, one atom per warp at a time: copies the record
+//   symfun_sweep_kernel  persistent, 9 warps per SM (216 registers), one atom per warp at a time: copies the record
 //                        (~10 KB, one coalesced pass) into shared memory and runs only the triple
 //                        loop (phases E, F) — the part that is FP64-pipe bound.
 //
 // Atoms are processed in chunks so that the records of a chunk (stride ~17 KB per atom for n <= 28)
 // stay a bounded scratch allocation; the extra HBM traffic is ~2 x 10 KB per atom on top of the 37 KB
-// block itself, on a kernel that uses ~13 % of the HBM bandwidth.
+// block itself, on kernels that keep DRAM ~29 % busy.  The per-atom code of both stages lives in
+// symfun_atom.cuh.
 //
 // Reference: Descriptor::generate_one_atom (sym_fn.cpp:416-602), sym_d_g2 / sym_d_g4 (:627-809).
 #include "symfun_atom.cuh"
