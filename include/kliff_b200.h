@@ -26,9 +26,10 @@
  *   - return value: 0 = ok; 1 = the reference's own error class for that call (singular cell,
  *     atom collision / cell grid too large — what neighbor_list_bind.cpp:68-72,205-209 turn into
  *     RuntimeError); other positive codes are KB_ERR_*; negative = -(cudaError_t).
- *   - no global mutable state apart from a relaxed-atomic launch counter (kb_launch_count):
- *     every function may be called from any host thread; one CUDA
- *     context (device) per process/rank is assumed.
+ *   - global mutable state: a relaxed-atomic launch counter (kb_launch_count), the one-time memory
+ *     pool setup, and — only while kb_kernel_timing is switched on — a mutex-guarded list of
+ *     recorded event pairs (open events are per host thread).  Every function may be called from
+ *     any host thread; one CUDA context (device) per process/rank is assumed.
  */
 #ifndef KLIFF_B200_H_
 #define KLIFF_B200_H_
@@ -176,8 +177,10 @@ void kb_batch_destroy(kb_batch_plan* plan, void* stream);
 #define KB_SYMFUN_GENERAL 1     /* global-atomics kernel: any neighbor count */
 #define KB_SYMFUN_TILED 2       /* CTA-per-atom shared-memory kernel: n <= 64, any families */
 #define KB_SYMFUN_WARP 3        /* warp-per-atom kernel: n <= 64, g1-g4 with zeta in {1,2,4,16}, lambda = +-1 */
-#define KB_SYMFUN_SPLIT 4       /* same domain as WARP, two launches: table kernel + triple-sweep kernel (AUTO's first choice) */
-#define KB_SYMFUN_WS 5          /* same domain, one warp-specialised kernel: table warps feed sweep warps inside each CTA */
+#define KB_SYMFUN_SPLIT 4       /* same domain as WARP, two launches: table kernel + triple-sweep kernel (round-1 sweep) */
+/* 5 was the warp-specialised single kernel of round 1 (measured 1.7x slower; removed from the build) */
+#define KB_SYMFUN_QUEUE 6       /* two launches, table kernel + queue sweep (fp64 blocks, shapes of set51 / set30:
+                                   AUTO's first choice); falls back to SPLIT's sweep elsewhere */
 
 int kb_symfun_block_offsets(int32_t n_centers, const int32_t* d_centers,
                             const int64_t* d_nl_offsets, int32_t n_desc, int64_t* d_dz_ptr,
@@ -229,7 +232,7 @@ int64_t kb_launch_count(int32_t reset);
 /* Per-kernel device times of the descriptor stage, measured with CUDA events on the launching
  * stream.  Returns in h_ms[4] / h_launches[4] (either may be NULL) the summed duration and number
  * of launches recorded since the previous call, by kernel: [0] symfun_prep_kernel, [1]
- * symfun_sweep_kernel, [2] fused symfun_warp_kernel, [3] symfun_ws_kernel; then switches recording on (enable != 0) or
+ * symfun_sweep_kernel / symfun_qsweep_kernel, [2] fused symfun_warp_kernel, [3] force_scatter / force_gather kernels; then switches recording on (enable != 0) or
  * off.  Off by default: no events are created unless a caller (bench.py) asks. */
 int kb_kernel_timing(int32_t enable, double* h_ms, int32_t* h_launches);
 

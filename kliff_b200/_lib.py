@@ -13,7 +13,7 @@ KB_MAX_GROUPS = 32
 KB_GROUP_WIDTH = 8
 
 KB_OK, KB_ERR_REFERENCE, KB_ERR_INVALID, KB_ERR_LIMIT, KB_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
-KB_SYMFUN_AUTO, KB_SYMFUN_GENERAL, KB_SYMFUN_TILED, KB_SYMFUN_WARP, KB_SYMFUN_SPLIT, KB_SYMFUN_WS = 0, 1, 2, 3, 4, 5
+KB_SYMFUN_AUTO, KB_SYMFUN_GENERAL, KB_SYMFUN_TILED, KB_SYMFUN_WARP, KB_SYMFUN_SPLIT, KB_SYMFUN_QUEUE = 0, 1, 2, 3, 4, 6
 KB_F64, KB_F32 = 0, 1
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libkliff_b200.so")

@@ -30,21 +30,20 @@ std::atomic<int> g_timing{0};
 std::mutex g_timing_mu;
 struct TimedLaunch { int tag; cudaEvent_t e0, e1; };
 std::vector<TimedLaunch> g_timed;
-cudaEvent_t g_open[KB_T_COUNT];
+thread_local cudaEvent_t t_open[KB_T_COUNT];  // begin/end pair up inside one host thread
 }  // namespace
 bool kb_timing_on() { return g_timing.load(std::memory_order_relaxed) != 0; }
 void kb_timing_begin(int tag, cudaStream_t st)
 {
   if (!kb_timing_on()) return;
-  std::lock_guard<std::mutex> lk(g_timing_mu);
-  cudaEventCreate(&g_open[tag]);
-  cudaEventRecord(g_open[tag], st);
+  cudaEventCreate(&t_open[tag]);
+  cudaEventRecord(t_open[tag], st);
 }
 void kb_timing_end(int tag, cudaStream_t st)
 {
   if (!kb_timing_on()) return;
   std::lock_guard<std::mutex> lk(g_timing_mu);
-  TimedLaunch t{tag, g_open[tag], nullptr};
+  TimedLaunch t{tag, t_open[tag], nullptr};
   cudaEventCreate(&t.e1);
   cudaEventRecord(t.e1, st);
   g_timed.push_back(t);

@@ -211,6 +211,7 @@ extern "C" int kb_force_scatter_fwd(int32_t n_centers, const int32_t* d_centers,
   if (n_centers == 0) return KB_OK;
   const int nblk = (n_centers + SC_WARPS - 1) / SC_WARPS;
   const size_t smem = sizeof(double) * SC_WARPS * n_desc;
+  kb_timing_begin(KB_T_SCATTER, kb_stream(stream));
   if (dz_dtype == KB_F64)
     force_scatter_kernel<false, double><<<nblk, SC_WARPS * 32, smem, kb_stream(stream)>>>(
         n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, n_desc, d_dEdG, d_scale,
@@ -219,6 +220,7 @@ extern "C" int kb_force_scatter_fwd(int32_t n_centers, const int32_t* d_centers,
     force_scatter_kernel<false, float><<<nblk, SC_WARPS * 32, smem, kb_stream(stream)>>>(
         n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, n_desc, d_dEdG, d_scale,
         static_cast<const float*>(d_dz), d_dz_ptr, d_forces);
+  kb_timing_end(KB_T_SCATTER, kb_stream(stream));
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -232,6 +234,7 @@ extern "C" int kb_force_scatter_bwd(int32_t n_centers, const int32_t* d_centers,
   if (n_centers < 0 || n_desc < 1 || (dz_dtype != KB_F64 && dz_dtype != KB_F32)) return KB_ERR_INVALID;
   if (n_centers == 0) return KB_OK;
   const int nblk = (n_centers + SC_WARPS - 1) / SC_WARPS;
+  kb_timing_begin(KB_T_SCATTER, kb_stream(stream));
   if (dz_dtype == KB_F64)
     force_gather_kernel<double><<<nblk, SC_WARPS * 32, 0, kb_stream(stream)>>>(
         n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, n_desc, d_gF, d_scale,
@@ -240,6 +243,7 @@ extern "C" int kb_force_scatter_bwd(int32_t n_centers, const int32_t* d_centers,
     force_scatter_kernel<true, float><<<nblk, SC_WARPS * 32, sizeof(double) * SC_WARPS * n_desc, kb_stream(stream)>>>(
         n_centers, d_centers, d_nl_offsets, d_nl_indices, d_image, n_desc, d_gF, d_scale,
         static_cast<const float*>(d_dz), d_dz_ptr, d_gdEdG);
+  kb_timing_end(KB_T_SCATTER, kb_stream(stream));
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

@@ -22,13 +22,7 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
                            const int32_t* d_subset, const double* d_coords, const int32_t* d_species,
                            const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn, double* d_zeta,
                            void* d_dz, int dz_dtype, const int64_t* d_dz_ptr, int32_t* d_overflow,
-                           bool* launched, bool* may_overflow, cudaStream_t st);
-
-int kb_symfun_ws_launch(const kb_symfun_params& P, int n_centers, const int32_t* d_centers,
-                        const int32_t* d_subset, const double* d_coords, const int32_t* d_species,
-                        const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn, double* d_zeta,
-                        void* d_dz, int dz_dtype, const int64_t* d_dz_ptr, int32_t* d_overflow,
-                        bool* launched, bool* may_overflow, cudaStream_t st);
+                           int variant, bool* launched, bool* may_overflow, cudaStream_t st);
 
 namespace {
 
@@ -115,7 +109,7 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
   // ---- preferred: warp-per-atom kernels (g4 sets with canonical exponents, n <= 64): the two-stage
   //      form first (table kernel + triple-sweep kernel), the fused kernel on request and for the
   //      atoms the first pass declines
-  if (mode == KB_SYMFUN_AUTO || mode == KB_SYMFUN_WARP || mode == KB_SYMFUN_SPLIT || mode == KB_SYMFUN_WS)
+  if (mode == KB_SYMFUN_AUTO || mode == KB_SYMFUN_WARP || mode == KB_SYMFUN_SPLIT || mode == KB_SYMFUN_QUEUE)
   {
     int32_t* ov = nullptr;
     KB_CUDA(cudaMallocAsync((void**) &ov, sizeof(int32_t) * ((size_t) n_centers + 2), st));
@@ -125,14 +119,10 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
       rc = kb_symfun_warp_launch(P, n_centers, d_centers, nullptr, d_coords, d_species, d_nl_offsets,
                                  d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov, 0, &launched,
                                  &may_overflow, st);
-    else if (mode == KB_SYMFUN_WS)
-      rc = kb_symfun_ws_launch(P, n_centers, d_centers, nullptr, d_coords, d_species, d_nl_offsets,
-                               d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov, &launched,
-                               &may_overflow, st);
-    else
+    else  // QUEUE: queue sweep where it applies, else the v3 sweep; AUTO / SPLIT: v3 (until the queue form wins)
       rc = kb_symfun_split_launch(P, n_centers, d_centers, nullptr, d_coords, d_species, d_nl_offsets,
-                                  d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov, &launched,
-                                  &may_overflow, st);
+                                  d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov,
+                                  mode == KB_SYMFUN_QUEUE ? 0 : 1, &launched, &may_overflow, st);
     if (rc == KB_OK && launched && may_overflow)
     {
       int32_t n_over = 0;

@@ -33,6 +33,10 @@ constexpr int PREP_WARPS = 4;
 #ifndef KB_SWEEP_REGS_NOGRAD
 #define KB_SWEEP_REGS_NOGRAD 128
 #endif
+#ifndef KB_QSWEEP_REGS
+#define KB_QSWEEP_REGS 255  // queue sweep (symfun_qsweep.cuh): 88 accumulators per lane; 8 warps per SM
+#endif
+#define KB_QSWEEP_MIN_BLOCKS (65536 / (32 * ((KB_QSWEEP_REGS + 7) & ~7)))
 #define KB_SWEEP_MIN_BLOCKS (65536 / (32 * KB_SWEEP_REGS))
 #define KB_SWEEP_MIN_BLOCKS_NOGRAD (65536 / (32 * KB_SWEEP_REGS_NOGRAD))
 #ifndef KB_PREP_MIN_BLOCKS
@@ -244,38 +248,22 @@ __device__ __forceinline__ void prep_tables(const PrepSmem& W, const kb_symfun_p
   __syncwarp();
 }
 
-// =============================================================================================
-// stage 1 for one atom: centre ordinal t -> record `rec` (header n = -1 when the atom is declined)
-// =============================================================================================
-template <bool GRAD, typename TOut>
-__device__ __forceinline__ void prep_atom(const kb_symfun_params& P, const SplitArgs& A, const RecLayout& L,
-                                          const PrepSmem& W, int t, unsigned char* rec, int lane)
+// ---- phases A + D of stage 1: pair-ij table (record) and the radial sets (final rows) ----------
+// Lanes = neighbors.  Returns the mask of neighbors within their species cutoff (sym_fn.cpp:451).
+// SOA selects the layout of the pair-ij table in the record: [NP][8] (two-stage sweep) or [8][NP]
+// (lane sweep, symfun_lane.cu).
+template <bool GRAD, typename TOut, bool SOA>
+__device__ __forceinline__ unsigned long long prep_pairs(const kb_symfun_params& P, const SplitArgs& A,
+                                                         const PrepSmem& W, int i, int si, int64_t off, int n,
+                                                         TOut* blk, double* zrow, double* gXYZ, double* gTJ,
+                                                         int lane)
 {
   const unsigned FULL = 0xffffffffu;
-  const int NP = A.NP, RC = A.RC, D = P.n_desc, NT = P.n_two, S = P.n_species;
-  double *XYZ = W.XYZ, *Z2 = W.Z2, *RCI = W.RCI, *R2LO = W.R2LO, *R2HI = W.R2HI;
-  unsigned long long* ADJ = W.ADJ;
-  int *SPC = W.SPC, *BASE = W.BASE;
-  unsigned short *JR = W.JR, *PAIR = W.PAIR;
-  unsigned char *JL = W.JL, *DEG = W.DEG, *KORD = W.KORD;
-  int* hdr = reinterpret_cast<int*>(rec);
-  const int i = A.centers ? A.centers[t] : t;
-  const int64_t off = A.nl_off[i];
-  const int n = (int) (A.nl_off[i + 1] - off);
-  if (n > NP)
-  {
-    if (lane == 0) { A.overflow[2 + atomicAdd(A.overflow, 1)] = t; hdr[0] = -1; hdr[1] = 0; }
-    return;
-  }
-  const int si = A.species[i];
-  const double xi = A.coords[3 * i], yi = A.coords[3 * i + 1], zi = A.coords[3 * i + 2];
+  const int NP = A.NP, NT = P.n_two, S = P.n_species;
+  double *XYZ = W.XYZ, *Z2 = W.Z2, *RCI = W.RCI;
+  int* SPC = W.SPC;
   const int row = 3 * (n + 1);
-  TOut* blk = GRAD ? static_cast<TOut*>(A.dz) + A.dz_ptr[t] : nullptr;
-  double* zrow = A.zeta + (int64_t) t * D;
-  double* gXYZ = reinterpret_cast<double*>(rec + L.xyz);
-  double* gTJ = reinterpret_cast<double*>(rec + L.tj);
-  double* gRK = reinterpret_cast<double*>(rec + L.rk);
-
+  const double xi = A.coords[3 * i], yi = A.coords[3 * i + 1], zi = A.coords[3 * i + 2];
   __syncwarp();
   for (int q = lane; q < 4 * NT; q += 32) Z2[q] = 0.0;
   __syncwarp();
@@ -304,9 +292,18 @@ __device__ __forceinline__ void prep_atom(const kb_symfun_params& P, const Split
       XYZ[jj] = xj; XYZ[NP + jj] = yj; XYZ[2 * NP + jj] = zj;
       gXYZ[jj] = xj; gXYZ[NP + jj] = yj; gXYZ[2 * NP + jj] = zj;
       SPC[jj] = sj;
-      double2* tj = reinterpret_cast<double2*>(gTJ + jj * SJ);
-      tj[0] = make_double2(r, r2x); tj[1] = make_double2(ir, fc);
-      tj[2] = make_double2(dfc, ux); tj[3] = make_double2(uy, uz);
+      if (SOA)
+      {
+        // field-major table [8][NP]: lanes = consecutive neighbors, so each field is one coalesced store
+        gTJ[jj] = r; gTJ[NP + jj] = r2x; gTJ[2 * NP + jj] = ir; gTJ[3 * NP + jj] = fc;
+        gTJ[4 * NP + jj] = dfc; gTJ[5 * NP + jj] = ux; gTJ[6 * NP + jj] = uy; gTJ[7 * NP + jj] = uz;
+      }
+      else
+      {
+        double2* tj = reinterpret_cast<double2*>(gTJ + jj * SJ);
+        tj[0] = make_double2(r, r2x); tj[1] = make_double2(ir, fc);
+        tj[2] = make_double2(dfc, ux); tj[3] = make_double2(uy, uz);
+      }
     }
     ACT |= (unsigned long long) __ballot_sync(FULL, act) << j0;
     for (int q0 = 0; q0 < NT; q0 += 4)
@@ -346,19 +343,19 @@ __device__ __forceinline__ void prep_atom(const kb_symfun_params& P, const Split
     }
   }
 
-  // ---- phase B: adjacency rows + per-slot lists (32-bit masks when every list fits in 32) ----
-  const int nrec = NP <= 32
-      ? build_lists<unsigned>(n, NP, S, (unsigned) ACT, XYZ, SPC, P.rcut, R2LO, R2HI,
-                              reinterpret_cast<unsigned*>(ADJ), BASE, DEG, JL, JR, PAIR, RC, lane)
-      : build_lists<unsigned long long>(n, NP, S, ACT, XYZ, SPC, P.rcut, R2LO, R2HI, ADJ, BASE, DEG, JL,
-                                        JR, PAIR, RC, lane);
-  if (nrec > RC)
-  {
-    if (lane == 0) { A.overflow[2 + atomicAdd(A.overflow, 1)] = t; hdr[0] = -1; hdr[1] = 0; }
-    return;
-  }
+  return ACT;
+}
 
-  // ---- phase C: pair-jk records; lanes = records, two per trip ---------------------------------
+// ---- phase C of stage 1: pair-jk records {r, 1/r, fc, dfc}; lanes = records, two per trip -------
+// SOA: field-major [4][stride] (lane sweep) instead of [nrec][4].
+template <bool SOA>
+__device__ __forceinline__ void prep_pair_records(const kb_symfun_params& P, const PrepSmem& W, int NP, int nrec,
+                                                  int stride, double* gRK, int lane)
+{
+  const int S = P.n_species;
+  const double *XYZ = W.XYZ, *RCI = W.RCI;
+  const int* SPC = W.SPC;
+  const unsigned short* PAIR = W.PAIR;
   for (int r0 = lane; r0 < nrec; r0 += 64)
   {
     const int r1 = r0 + 32;
@@ -376,16 +373,29 @@ __device__ __forceinline__ void prep_atom(const kb_symfun_params& P, const Split
     const int pa = SPC[ja] * S + SPC[ka], pb2 = SPC[jb] * S + SPC[kb];
     kb_cutoff_fast(ra, P.rcut[pa], RCI[pa], fca, dfca);
     kb_cutoff_fast(rb, P.rcut[pb2], RCI[pb2], fcb, dfcb);
-    double2* rka = reinterpret_cast<double2*>(gRK + r0 * SR);
-    rka[0] = make_double2(ra, ira); rka[1] = make_double2(fca, dfca);
-    if (two)
+    if (SOA)
     {
-      double2* rkb = reinterpret_cast<double2*>(gRK + r1 * SR);
-      rkb[0] = make_double2(rb, irb); rkb[1] = make_double2(fcb, dfcb);
+      gRK[r0] = ra; gRK[stride + r0] = ira; gRK[2 * stride + r0] = fca; gRK[3 * stride + r0] = dfca;
+      if (two) { gRK[r1] = rb; gRK[stride + r1] = irb; gRK[2 * stride + r1] = fcb; gRK[3 * stride + r1] = dfcb; }
+    }
+    else
+    {
+      double2* rka = reinterpret_cast<double2*>(gRK + r0 * SR);
+      rka[0] = make_double2(ra, ira); rka[1] = make_double2(fca, dfca);
+      if (two)
+      {
+        double2* rkb = reinterpret_cast<double2*>(gRK + r1 * SR);
+        rkb[0] = make_double2(rb, irb); rkb[1] = make_double2(fcb, dfcb);
+      }
     }
   }
 
-  // ---- phase S: slots ordered by adjacency degree (descending, index as tie-break) ---------
+}
+
+// ---- phase S of stage 1: slots ordered by adjacency degree (descending, index as tie-break) ----
+__device__ __forceinline__ void prep_sort_slots(int n, const unsigned char* DEG, unsigned char* KORD, int lane)
+{
+  const unsigned FULL = 0xffffffffu;
   if (n <= 32)
   {
     // one slot per lane, degrees < 32: bit-serial ballots from the top bit down leave in `tied` the
@@ -411,6 +421,57 @@ __device__ __forceinline__ void prep_atom(const kb_symfun_params& P, const Split
       KORD[rank] = (unsigned char) k;
     }
   __syncwarp();
+
+}
+
+// =============================================================================================
+// stage 1 for one atom: centre ordinal t -> record `rec` (header n = -1 when the atom is declined)
+// =============================================================================================
+template <bool GRAD, typename TOut>
+__device__ __forceinline__ void prep_atom(const kb_symfun_params& P, const SplitArgs& A, const RecLayout& L,
+                                          const PrepSmem& W, int t, unsigned char* rec, int lane)
+{
+  const unsigned FULL = 0xffffffffu;
+  const int NP = A.NP, RC = A.RC, D = P.n_desc, NT = P.n_two, S = P.n_species;
+  double *XYZ = W.XYZ, *Z2 = W.Z2, *RCI = W.RCI, *R2LO = W.R2LO, *R2HI = W.R2HI;
+  unsigned long long* ADJ = W.ADJ;
+  int *SPC = W.SPC, *BASE = W.BASE;
+  unsigned short *JR = W.JR, *PAIR = W.PAIR;
+  unsigned char *JL = W.JL, *DEG = W.DEG, *KORD = W.KORD;
+  int* hdr = reinterpret_cast<int*>(rec);
+  const int i = A.centers ? A.centers[t] : t;
+  const int64_t off = A.nl_off[i];
+  const int n = (int) (A.nl_off[i + 1] - off);
+  if (n > NP)
+  {
+    if (lane == 0) { A.overflow[2 + atomicAdd(A.overflow, 1)] = t; hdr[0] = -1; hdr[1] = 0; }
+    return;
+  }
+  const int si = A.species[i];
+  TOut* blk = GRAD ? static_cast<TOut*>(A.dz) + A.dz_ptr[t] : nullptr;
+  double* zrow = A.zeta + (int64_t) t * D;
+  double* gXYZ = reinterpret_cast<double*>(rec + L.xyz);
+  double* gTJ = reinterpret_cast<double*>(rec + L.tj);
+  double* gRK = reinterpret_cast<double*>(rec + L.rk);
+
+  const unsigned long long ACT =
+      prep_pairs<GRAD, TOut, false>(P, A, W, i, si, off, n, blk, zrow, gXYZ, gTJ, lane);
+
+  // ---- phase B: adjacency rows + per-slot lists (32-bit masks when every list fits in 32) ----
+  const int nrec = NP <= 32
+      ? build_lists<unsigned>(n, NP, S, (unsigned) ACT, XYZ, SPC, P.rcut, R2LO, R2HI,
+                              reinterpret_cast<unsigned*>(ADJ), BASE, DEG, JL, JR, PAIR, RC, lane)
+      : build_lists<unsigned long long>(n, NP, S, ACT, XYZ, SPC, P.rcut, R2LO, R2HI, ADJ, BASE, DEG, JL,
+                                        JR, PAIR, RC, lane);
+  if (nrec > RC)
+  {
+    if (lane == 0) { A.overflow[2 + atomicAdd(A.overflow, 1)] = t; hdr[0] = -1; hdr[1] = 0; }
+    return;
+  }
+
+  prep_pair_records<false>(P, W, NP, nrec, 0, gRK, lane);
+
+  prep_sort_slots(n, DEG, KORD, lane);
 
   // ---- record: lists, order, header ----------------------------------------------------------
   {

@@ -22,6 +22,7 @@
 //
 // Reference: Descriptor::generate_one_atom (sym_fn.cpp:416-602), sym_d_g2 / sym_d_g4 (:627-809).
 #include "symfun_atom.cuh"
+#include "symfun_qsweep.cuh"
 
 #include <cstdlib>
 
@@ -107,6 +108,89 @@ symfun_sweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs 
   }
 }
 
+
+// =============================================================================================
+// stage 2, queue form (symfun_qsweep.cuh): fp64 blocks with gradient, parameter shapes SH
+// =============================================================================================
+template <class SH>
+__global__ void __maxnreg__(KB_QSWEEP_REGS)
+symfun_qsweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const unsigned FULL = 0xffffffffu;
+  const RecLayout L = rec_layout(A.NP, A.RC);
+  const QSmem W = qsweep_carve(smem_raw, L);
+  qsweep_tables<SH>(P, W, smem_raw, L.bytes, lane);
+  const unsigned sbase = (unsigned) __cvta_generic_to_shared(smem_raw);
+
+  // record -> shared memory with asynchronous 16-byte copies (all in flight at once)
+  auto copy_record = [&](int tt, int nrec) {
+    const unsigned char* rec = A.records + (size_t) (tt - A.lo) * L.bytes;
+    const int words = (L.rk + 32 * nrec) >> 4;
+    for (int q = lane; q < words; q += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * q), "l"(rec + 16 * (size_t) q) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto grab = [&]() {
+    int v = 0;
+    if (lane == 0) v = A.lo + atomicAdd(A.work, 1);
+    return __shfl_sync(FULL, v, 0);
+  };
+  auto header = [&](int tt) {
+    return tt < A.hi ? __ldcg(reinterpret_cast<const int4*>(A.records + (size_t) (tt - A.lo) * L.bytes))
+                     : make_int4(-1, 0, 0, 0);
+  };
+
+  // Atoms are grabbed two ahead: `cur` is swept, the record of `nxt` is copied while the centre slots
+  // of `cur` are read back, the header of `nx2` is in flight and its record on its way into L2.
+  int cur = grab();
+  int4 hcur = header(cur);
+  int nxt = grab();
+  int4 hnxt = header(nxt);
+  if (cur < A.hi && hcur.x >= 0) copy_record(cur, hcur.y);
+  while (cur < A.hi)
+  {
+    const int nx2 = grab();
+    const int4 hnx2 = header(nx2);
+    if (nx2 < A.hi)
+    {
+      const unsigned char* nx = A.records + (size_t) (nx2 - A.lo) * L.bytes;
+      const int lines = (L.rk + 16 * A.RC + 127) >> 7;
+      for (int q = lane; q < lines; q += 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + ((size_t) q << 7)));
+    }
+    const int t = A.subset ? A.subset[cur] : cur;
+    const int n = hcur.x;
+    if (n >= 0)  // else: declined by stage 1
+    {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      qsweep_atom<SH>(P, A, W, t, n, lane);
+      __syncwarp();
+    }
+    if (nxt < A.hi && hnxt.x >= 0) copy_record(nxt, hnxt.y);
+    if (n >= 0) qsweep_centre<SH>(P, A, W, t, n, lane);
+    cur = nxt; hcur = hnxt;
+    nxt = nx2; hnxt = hnx2;
+  }
+}
+
+using QShape51 = QShape<7, 0, 0, 3, 3>;  // set51: zeta 1, 2 on all 7 eta, zeta 4, 16 on the last 4
+using QShape30 = QShape<6, 0, 0, 3, 3>;  // set30
+
+// 0: the queue sweep does not cover this parameter set; 1: QShape51; 2: QShape30
+int qsweep_shape(const kb_symfun_params& P)
+{
+  const int NE = P.n_groups;
+  if (NE != 7 && NE != 6) return 0;
+  const int lo_need[4] = {0, 0, 3, 3};
+  for (int z = 0; z < 4; z++)
+    for (int g = 0; g < lo_need[z]; g++)
+      if (P.grp_out[g][2 * z] >= 0 || P.grp_out[g][2 * z + 1] >= 0) return 0;
+  return NE == 7 ? 1 : 2;
+}
+
 }  // namespace
 
 // Returns KB_OK and *launched = true when the parameter set is one these kernels handle.  Atoms
@@ -116,7 +200,7 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
                            const int32_t* d_subset, const double* d_coords, const int32_t* d_species,
                            const int64_t* d_nl_off, const int32_t* d_nl_idx, int maxn, double* d_zeta,
                            void* d_dz, int dz_dtype, const int64_t* d_dz_ptr, int32_t* d_overflow,
-                           bool* launched, bool* may_overflow, cudaStream_t st)
+                           int variant, bool* launched, bool* may_overflow, cudaStream_t st)
 {
   *launched = false;
   *may_overflow = false;
@@ -132,11 +216,15 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
   NP = (NP + 1) & ~1;
   const int worst = NP * (NP - 1) / 2;
   const bool grad = d_dz != nullptr;
+  // variant 0: the queue sweep where it applies (fp64 blocks with gradient, shapes of set51 / set30);
+  // variant 1: always the v3 sweep
+  const int qshape = (variant == 0 && grad && dz_dtype == KB_F64) ? qsweep_shape(P) : 0;
   const size_t limit = 227 * 1024, per_block_reserve = 1024;
-  const size_t extra = (size_t) SC_DOUBLES * 8 + 64 * 8;
+  const size_t extra = qshape ? qsweep_extra_bytes(qshape == 1 ? QShape51::NI : QShape30::NI)
+                              : (size_t) SC_DOUBLES * 8 + 64 * 8;
   // record capacity: worst case when that still leaves the wanted residency, else what fits (never
   // below 45 % of the worst case: a filled sphere has ~44 % of its neighbor pairs within the cutoff)
-  const int want = grad ? KB_SWEEP_MIN_BLOCKS : KB_SWEEP_MIN_BLOCKS_NOGRAD;
+  const int want = qshape ? KB_QSWEEP_MIN_BLOCKS : grad ? KB_SWEEP_MIN_BLOCKS : KB_SWEEP_MIN_BLOCKS_NOGRAD;
   int RC = worst;
   {
     const size_t budget = limit / want - per_block_reserve;
@@ -200,8 +288,9 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
     // 29 % busy.  The cost is not the store path (the same zeros sent as cp.async.bulk copies measure
     // identically); the row pieces themselves get slower once they land on resident dirty lines.
     // KB_PREZERO=1 switches it on.
+    // The queue sweep always zeroes first (its centre-slot read-back wants the rows resident in L2).
     const char* pz = getenv("KB_PREZERO");
-    if (!(pz && pz[0] == '1')) A.ang_lo = A.ang_hi = 0;
+    if (!qshape && !(pz && pz[0] == '1')) A.ang_lo = A.ang_hi = 0;
   }
 
   int per_sm = (int) (limit / (sweep_smem + per_block_reserve));
@@ -231,6 +320,23 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
     symfun_sweep_kernel<G, T><<<sgrid, 32, sweep_smem, st>>>(P, A);                                    \
     kb_timing_end(KB_T_SWEEP, st);                                                                     \
   } while (0)
+#define KB_QSPLIT_LAUNCH(SH)                                                                           \
+  do {                                                                                                 \
+    cudaError_t e_ = cudaFuncSetAttribute(symfun_prep_kernel<true, double>,                            \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+                                          (int) (prep_warp * PREP_WARPS));                             \
+    if (e_ == cudaSuccess)                                                                             \
+      e_ = cudaFuncSetAttribute(symfun_qsweep_kernel<SH>,                                              \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sweep_smem);        \
+    if (e_ != cudaSuccess) { rc = -(int) e_; break; }                                                  \
+    kb_timing_begin(KB_T_PREP, st);                                                                    \
+    symfun_prep_kernel<true, double><<<pgrid, PREP_WARPS * 32, prep_warp * PREP_WARPS, st>>>(          \
+        P, A, (int) prep_warp);                                                                        \
+    kb_timing_end(KB_T_PREP, st);                                                                      \
+    kb_timing_begin(KB_T_SWEEP, st);                                                                   \
+    symfun_qsweep_kernel<SH><<<sgrid, 32, sweep_smem, st>>>(P, A);                                     \
+    kb_timing_end(KB_T_SWEEP, st);                                                                     \
+  } while (0)
   for (int c = 0; c < n_chunks && rc == KB_OK; c++)
   {
     A.lo = c * chunk;
@@ -241,7 +347,9 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
     if (pgrid > sms * 16) pgrid = sms * 16;
     int sgrid = sms * per_sm;
     if (sgrid > cnt) sgrid = cnt;
-    if (!grad) KB_SPLIT_LAUNCH(false, double);
+    if (qshape == 1) KB_QSPLIT_LAUNCH(QShape51);
+    else if (qshape == 2) KB_QSPLIT_LAUNCH(QShape30);
+    else if (!grad) KB_SPLIT_LAUNCH(false, double);
     else if (dz_dtype == KB_F32) KB_SPLIT_LAUNCH(true, float);
     else KB_SPLIT_LAUNCH(true, double);
     if (rc == KB_OK)
@@ -252,6 +360,7 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
     }
   }
 #undef KB_SPLIT_LAUNCH
+#undef KB_QSPLIT_LAUNCH
   cudaFreeAsync(records, st);
   cudaFreeAsync(work, st);
   if (rc == KB_OK) *launched = true;

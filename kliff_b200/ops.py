@@ -365,8 +365,8 @@ def launch_count(reset=False):
 
 def kernel_timing(enable):
     """Collects the per-kernel device times recorded since the last call and switches recording
-    on/off.  Returns {"prep": (ms, launches), "sweep": (...), "fused": (...), "ws": (...)}."""
+    on/off.  Returns {"prep": (ms, launches), "sweep": (...), "fused": (...), "scatter": (...)}."""
     ms = (C.c_double * 4)()
     cnt = (C.c_int32 * 4)()
     check(_lib.lib().kb_kernel_timing(int(bool(enable)), ms, cnt), "kb_kernel_timing")
-    return {name: (ms[q], cnt[q]) for q, name in enumerate(("prep", "sweep", "fused", "ws"))}
+    return {name: (ms[q], cnt[q]) for q, name in enumerate(("prep", "sweep", "fused", "scatter"))}
