@@ -34,9 +34,9 @@ constexpr int PREP_WARPS = 4;
 #define KB_SWEEP_REGS_NOGRAD 128
 #endif
 #ifndef KB_QSWEEP_REGS
-#define KB_QSWEEP_REGS 255  // queue sweep (symfun_qsweep.cuh): 88 accumulators per lane; 8 warps per SM
+#define KB_QSWEEP_REGS 255  // queue sweep (symfun_qsweep.cuh): 88 accumulators per sweep lane; 4 warp pairs per SM
 #endif
-#define KB_QSWEEP_MIN_BLOCKS (65536 / (32 * ((KB_QSWEEP_REGS + 7) & ~7)))
+#define KB_QSWEEP_MIN_BLOCKS (65536 / (64 * ((KB_QSWEEP_REGS + 7) & ~7)))  // CTAs of two warps
 #define KB_SWEEP_MIN_BLOCKS (65536 / (32 * KB_SWEEP_REGS))
 #define KB_SWEEP_MIN_BLOCKS_NOGRAD (65536 / (32 * KB_SWEEP_REGS_NOGRAD))
 #ifndef KB_PREP_MIN_BLOCKS

@@ -117,63 +117,24 @@ __global__ void __maxnreg__(KB_QSWEEP_REGS)
 symfun_qsweep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x;
-  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const RecLayout L = rec_layout(A.NP, A.RC);
-  const QSmem W = qsweep_carve(smem_raw, L);
-  qsweep_tables<SH>(P, W, smem_raw, L.bytes, lane);
-  const unsigned sbase = (unsigned) __cvta_generic_to_shared(smem_raw);
-
-  // record -> shared memory with asynchronous 16-byte copies (all in flight at once)
-  auto copy_record = [&](int tt, int nrec) {
-    const unsigned char* rec = A.records + (size_t) (tt - A.lo) * L.bytes;
-    const int words = (L.rk + 32 * nrec) >> 4;
-    for (int q = lane; q < words; q += 32)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + 16u * q), "l"(rec + 16 * (size_t) q) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  auto grab = [&]() {
-    int v = 0;
-    if (lane == 0) v = A.lo + atomicAdd(A.work, 1);
-    return __shfl_sync(FULL, v, 0);
-  };
-  auto header = [&](int tt) {
-    return tt < A.hi ? __ldcg(reinterpret_cast<const int4*>(A.records + (size_t) (tt - A.lo) * L.bytes))
-                     : make_int4(-1, 0, 0, 0);
-  };
-
-  // Atoms are grabbed two ahead: `cur` is swept, the record of `nxt` is copied while the centre slots
-  // of `cur` are read back, the header of `nx2` is in flight and its record on its way into L2.
-  int cur = grab();
-  int4 hcur = header(cur);
-  int nxt = grab();
-  int4 hnxt = header(nxt);
-  if (cur < A.hi && hcur.x >= 0) copy_record(cur, hcur.y);
-  while (cur < A.hi)
+  const QSmem W = qsweep_carve(smem_raw, L, SH::NI);
+  qsweep_tables<SH>(P, W, smem_raw, L.bytes, threadIdx.x);
+  __syncthreads();
+  // Roles: the two warps of a CTA normally sit in adjacent hardware warp slots, i.e. on neighbouring
+  // schedulers; alternating the assignment with bit 2 of the slot number puts one helper and one sweep
+  // warp on every scheduler when four CTAs share an SM.  (Any assignment is correct; this one balances.)
+  if (threadIdx.x == 0)
   {
-    const int nx2 = grab();
-    const int4 hnx2 = header(nx2);
-    if (nx2 < A.hi)
-    {
-      const unsigned char* nx = A.records + (size_t) (nx2 - A.lo) * L.bytes;
-      const int lines = (L.rk + 16 * A.RC + 127) >> 7;
-      for (int q = lane; q < lines; q += 32)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + ((size_t) q << 7)));
-    }
-    const int t = A.subset ? A.subset[cur] : cur;
-    const int n = hcur.x;
-    if (n >= 0)  // else: declined by stage 1
-    {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
-      qsweep_atom<SH>(P, A, W, t, n, lane);
-      __syncwarp();
-    }
-    if (nxt < A.hi && hnxt.x >= 0) copy_record(nxt, hnxt.y);
-    if (n >= 0) qsweep_centre<SH>(P, A, W, t, n, lane);
-    cur = nxt; hcur = hnxt;
-    nxt = nx2; hnxt = hnx2;
+    unsigned slot;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(slot));
+    W.SYNC[3] = (int) (((slot >> 2) ^ slot) & 1u);
   }
+  __syncthreads();
+  const int role = warp == 0 ? W.SYNC[3] : 1 - W.SYNC[3];
+  if (role == 0) q_sweeper<SH>(P, A, W, lane);
+  else q_helper<SH>(P, A, L, W, smem_raw, lane);
 }
 
 using QShape51 = QShape<7, 0, 0, 3, 3>;  // set51: zeta 1, 2 on all 7 eta, zeta 4, 16 on the last 4
@@ -334,7 +295,7 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
         P, A, (int) prep_warp);                                                                        \
     kb_timing_end(KB_T_PREP, st);                                                                      \
     kb_timing_begin(KB_T_SWEEP, st);                                                                   \
-    symfun_qsweep_kernel<SH><<<sgrid, 32, sweep_smem, st>>>(P, A);                                     \
+    symfun_qsweep_kernel<SH><<<sgrid, 64, sweep_smem, st>>>(P, A);                                     \
     kb_timing_end(KB_T_SWEEP, st);                                                                     \
   } while (0)
   for (int c = 0; c < n_chunks && rc == KB_OK; c++)
