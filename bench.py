@@ -10,6 +10,20 @@ One step = one pass of the hot path over that supercell: padding atoms -> cell-l
 list -> symmetry functions + dG/dr (packed, materialised in HBM).
 metric = descriptor+dG/dr atoms/sec.  For N > 1 every rank runs the pass on its own supercell
 (weak scaling, no data-path collective); timing is per-step CUDA events, max over ranks.
+
+The same JSON line also carries the two multi-GPU paths of the metric's second half, timed in the
+same run at every N:
+  "slab"         ONE supercell of 48^3 cells (884 736 atoms, fits one GPU) split over the N ranks by
+                 spatial domain with ghost halos: NCCL halo exchange + descriptors + forces + reverse
+                 force exchange inside the step (strong scaling); at N = 8 also BASELINE.json's
+                 configs[3]-sized cell (10 M atoms).
+  "train_epoch"  synthetic 20 000-configuration Si set (configs[4] scaled to minutes): sharded create(),
+                 then optimisation epochs with one gradient all-reduce per step; graph capture / warm-up
+                 outside the timed region.
+
+--impl reference runs the UNMODIFIED reference package (baseline/_ref, built by baseline/build_ref.sh)
+through its own driver: kliff.parallel.parmap1(SymmetryFunction.transform, ...) for the descriptors
+and CalculatorTorch(gpu=False) + Loss.minimize for the epoch (baseline/ref_runner.py).
 """
 import argparse
 import json
@@ -28,10 +42,23 @@ if ROOT not in sys.path:
 A_SI, SIGMA, RC = 5.431, 0.05, 5.0
 FLOP_CANON = 380618.0   # per atom, set51 / n=28 / T=378 / T4=168
 BYTES_CANON = 36724.0   # per atom, fp64 zeta + dG/dr written + inputs read once
-# dram__bytes_read.sum + dram__bytes_write.sum of the descriptor stage on this very workload
-# (1 000 000 atoms: 4 chunks x (symfun_prep_kernel + symfun_sweep_kernel)), ncu --set full capture
-# of round 1: profiles/r01_ncu_symfun_split_1M_traffic.txt
-TRAFFIC_NCU_BYTES_PER_ATOM = 82207.7
+BYTES_SCATTER = 36044.0  # per atom and direction of the force contraction: 8 D 3 (n+1) block + weights + indices
+# dram__bytes_read.sum + dram__bytes_write.sum of the descriptor stage on this very workload come from
+# an ncu --set full capture of the same command (a number taken under a profiler cannot be a bench value,
+# and DRAM counters are not readable without one): scripts/ncu_traffic.py parses the capture and writes
+# profiles/traffic_1M.json, which is read here.
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic_1M.json")
+
+
+def ncu_traffic(nx):
+    """(bytes per step, source) from the committed ncu capture of this workload, or (None, reason)."""
+    try:
+        d = json.load(open(TRAFFIC_FILE))
+        if int(d.get("nx", -1)) != nx:
+            return None, f"no capture for nx={nx}"
+        return float(d["dram_bytes_per_step"]), d.get("source", TRAFFIC_FILE)
+    except Exception as e:
+        return None, f"no capture ({e})"
 
 
 def diamond(nx, seed):
@@ -161,44 +188,88 @@ class CpuBaseline:
         self.pool.join()
 
 
+def ref_run(what, timeout=1500, **kw):
+    """Runs baseline/ref_runner.py (the unmodified reference, own process) and returns its JSON."""
+    src = os.path.join(ROOT, "baseline", "_ref", "kliff_src")
+    if not os.path.isdir(os.path.join(src, "kliff")):
+        raise RuntimeError("baseline/_ref is not built (baseline/build_ref.sh needs /root/reference)")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = src + os.pathsep + os.path.join(ROOT, "baseline", "stubs")
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    cmd = [sys.executable, "-W", "ignore", os.path.join(ROOT, "baseline", "ref_runner.py"), what]
+    for k, v in kw.items():
+        cmd += [f"--{k}", str(v)]
+    r = subprocess.run(cmd, env=env, cwd="/tmp", capture_output=True, text=True, timeout=timeout)
+    for line in r.stdout.splitlines():
+        if line.startswith("REF_JSON "):
+            return json.loads(line[9:])
+    raise RuntimeError(f"reference run failed (rc {r.returncode}): {r.stderr[-400:]}")
+
+
+REF_NX = 3  # sample configurations of the reference arm: 3^3 cells = 216 atoms (its dense dG/dr is 57 MB each)
+
+
+def reference_descriptor_sample(cores, repeat):
+    """The reference's own driver (kliff/legacy/descriptors/descriptor.py:234-236) on `cores` processes
+    over 2 x cores sample configurations; returns (atoms/s, description, raw)."""
+    out = ref_run("descriptor", nx=REF_NX, configs=2 * cores, nprocs=cores, repeat=repeat)
+    text = (f"{out['configs']} jittered diamond-Si cells of {out['atoms_per_config']} atoms (same lattice, cutoff, "
+            f"set51 as the job; the reference's dense (N, D, 3N) output rules out larger cells) through "
+            f"kliff.parallel.parmap1(SymmetryFunction.transform, fit_forces=True), nprocs={out['nprocs']}: "
+            f"paddings, neighbor list, C++ generate_one_atom and the Python scatter into the dense arrays included")
+    return out["atoms_per_s"], text, out
+
+
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's C++ descriptor path on the host cores (rank 0 only)."""
+    """--impl reference: the unmodified reference through its own driver on the host cores (rank 0 only)."""
     if rank != 0:
         return
-    base = CpuBaseline(nx=12)
-    per_core = 470.0  # atoms/s/core measured for the reference in the build container (BASELINE.md §2)
-    sample = int(max(2000, min(200000, per_core * base.cores * 4.0)))  # ~4 s per step
-    for _ in range(max(1, min(args.warmup, 1))):
-        base.run(max(base.cores * 8, sample // 8))
-    rates, t0 = [], time.time()
-    for _ in range(args.steps):
-        rates.append(base.run(sample))
-    wall = time.time() - t0
-    base.close()
-    value = sample * args.steps / wall
+    cores = len(os.sched_getaffinity(0))
     natoms_job = 8 * args.nx ** 3
-    line = {
-        "impl": "reference", "metric": "descriptor+dG/dr atoms/sec", "value": value, "unit": "atoms/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"diamond-Si {natoms_job}-atom supercell, set51, cos 5.0 A, neighbor list + "
-                               "descriptor + dG/dr (configs[1])", "nx": args.nx},
-        "cpu_baseline": {"value": value, "unit": "atoms/s", "cores": base.cores, "kind": base.kind,
-                         "sample": f"{sample} atoms per step of a {base.n}-atom jittered diamond cell "
-                                   f"(same lattice/cutoff/set51 as the job), generate_one_atom(grad=True) over "
-                                   f"{base.cores} forked workers; serial paddings+neighbor list "
-                                   f"{base.t_neigh:.2f} s not included"},
-        "e2e": {"value": value, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    line = {"impl": "reference", "metric": "descriptor+dG/dr atoms/sec", "unit": "atoms/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "gpu_launches": 0}
+    try:
+        t0 = time.time()
+        rate, text, out = reference_descriptor_sample(cores, repeat=args.steps + min(args.warmup, 1))
+        secs = out["seconds"][min(args.warmup, 1):]
+        value = out["atoms"] * len(secs) / sum(secs)
+        line.update({
+            "value": value, "ms_per_step": 1e3 * sum(secs) / len(secs),
+            "config": {"workload": f"diamond-Si {natoms_job}-atom supercell, set51, cos 5.0 A, neighbor list + "
+                                   f"descriptor + dG/dr (configs[1]) — SAMPLED: each step = {text}",
+                       "nx": args.nx},
+            "cpu_baseline": {"value": value, "unit": "atoms/s", "cores": cores, "kind": "reference", "sample": text},
+            "e2e": {"value": value, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        try:  # second half of the metric: the reference's training epoch on CPU torch
+            ep = ref_run("epoch", configs=200, nprocs=cores, epochs=1)
+            line["train_epoch"] = {
+                "configs": ep["configs"], "create_s": ep["create_s"], "epoch_s": ep["epoch_s"],
+                "per_config_ms": {"create": 1e3 * ep["create_s"] / ep["configs"],
+                                  "epoch": 1e3 * ep["epoch_s"] / ep["configs"]}, "what": ep["what"]}
+        except Exception as e:
+            line["train_epoch"] = {"error": str(e)}
+    except Exception as e:
+        line = {"impl": "reference", "unavailable": str(e).splitlines()[0][:200]}
     print(json.dumps(line))
 
 
-def run_slab_workload(args, rank, world, dev):
-    """One periodic supercell of (world * nx) x nx x nx cells, slab r owned by rank r.  Step =
-    halo exchange (NCCL p2p) -> paddings along a2/a3 -> neighbor list -> descriptor + dG/dr of the
-    owned atoms -> force contraction with a fixed dE/dG -> reverse halo exchange of ghost forces."""
+def slab_block(nxs, ny, x0_cells, seed):
+    """Jittered diamond block of nxs x ny x ny conventional cells starting x0_cells along a1."""
+    basis = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0],
+                      [.25, .25, .25], [.25, .75, .75], [.75, .25, .75], [.75, .75, .25]])
+    g = np.stack(np.meshgrid(np.arange(nxs), np.arange(ny), np.arange(ny), indexing="ij"), -1).reshape(-1, 3)
+    pos = (g[:, None, :] + basis[None]).reshape(-1, 3) * A_SI
+    pos += np.random.default_rng(seed).normal(0.0, SIGMA, pos.shape)
+    pos[:, 0] += A_SI * x0_cells + A_SI / 8.0   # the 1/8-cell shift keeps jittered atoms off the slab faces
+    return np.ascontiguousarray(pos)
+
+
+def slab_probe(nx_total, ny, rank, world, dev, steps, warmup=3):
+    """ONE periodic supercell of nx_total x ny x ny cells, slab r (nx_total / world cells thick) owned by
+    rank r.  Step = halo exchange (NCCL p2p) -> paddings along a2/a3 -> neighbor list -> descriptor +
+    dG/dr of the owned atoms -> force contraction with a fixed dE/dG -> reverse halo exchange of the
+    ghost forces.  All ranks call this; times are CUDA events, max over ranks."""
     import torch
     import torch.distributed as dist
 
@@ -206,18 +277,15 @@ def run_slab_workload(args, rank, world, dev):
     from kliff_b200.legacy.descriptors import SymmetryFunction
     from kliff_b200.parallel import SlabDecomposition
 
-    nx = args.nx
-    cell = np.diag([A_SI * nx * world, A_SI * nx, A_SI * nx])
-    _, pos = diamond(nx, seed=rank)
-    pos[:, 0] += A_SI * nx * rank + A_SI / 8.0  # this rank's slab of the global lattice; the 1/8-cell
-    #                                             shift keeps jittered atoms off the slab boundaries
-    n = len(pos)
+    assert nx_total % world == 0
+    nxs = nx_total // world
+    cell = np.diag([A_SI * nx_total, A_SI * ny, A_SI * ny])
+    pos = slab_block(nxs, ny, rank * nxs, seed=rank)
     desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": RC}, hyperparams="set51", normalize=False,
                             dtype=np.float64)
     dd = SlabDecomposition(cell, [1, 1, 1], RC, rank=rank, world=world)
     x_own = dd.wrap(torch.tensor(pos, device=dev))
-    owner = dd.owner(x_own)
-    keep = owner == rank                       # jitter can push a face atom across the slab boundary:
+    keep = dd.owner(x_own) == rank             # jitter can push a face atom across the slab boundary:
     moved = int((~keep).sum())                 # such atoms are simply not simulated (counted below)
     x_own = x_own[keep].contiguous()
     n_own = x_own.shape[0]
@@ -236,14 +304,14 @@ def run_slab_workload(args, rank, world, dev):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         fp, F, ng = step()
         del fp
         flush.fill_(1)
     barrier()
     launches0 = ops.launch_count()
     ms = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.fill_(0)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -262,18 +330,29 @@ def run_slab_workload(args, rank, world, dev):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     total_ms, atoms = float(tmax[0]), float(tot[1])
+    del flush, w, x_own
+    torch.cuda.empty_cache()
+    return {"workload": f"ONE diamond-Si supercell of {nx_total}x{ny}x{ny} cells, slab of {nxs} cells per GPU, "
+                        f"halo {RC} A, NCCL halo + reverse force exchange inside the step",
+            "atoms": int(atoms), "n_gpus": world, "ms_per_step": total_ms / steps,
+            "atoms_per_s": atoms * steps / (total_ms * 1e-3), "steps": steps,
+            "atoms_rank0": n_own, "ghosts_rank0": int(ng), "paddings_rank0": int(npad),
+            "local_atoms_rank0": int(nloc), "atoms_dropped_at_faces_rank0": moved,
+            "net_force_max_abs": float(tot[2]), "gpu_launches": int(launches),
+            "l2": "256 MiB write between timed steps"}
+
+
+def run_slab_workload(args, rank, world, dev):
+    """--workload slab: weak-scaling form (nx cells per GPU along a1), one JSON line of its own."""
+    r = slab_probe(args.nx * world, args.nx, rank, world, dev, args.steps, max(args.warmup, 3))
     if rank == 0:
         print(json.dumps({
             "metric": "descriptor+dG/dr+forces atoms/sec (one supercell, spatial domains + ghost halos)",
-            "value": atoms * args.steps / (total_ms * 1e-3), "unit": "atoms/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"ONE diamond-Si supercell of {world * nx}x{nx}x{nx} cells ({int(atoms)} atoms), "
-                                   f"slab per GPU, halo {RC} A (BASELINE.json configs[3] style)",
-                       "atoms_per_gpu": n_own, "ghosts_rank0": int(ng), "paddings_rank0": int(npad),
-                       "local_atoms_rank0": int(nloc), "atoms_dropped_at_faces_rank0": moved,
-                       "l2": "256 MiB write between timed steps"},
-            "gpu_launches": int(launches)}))
+            "value": r["atoms_per_s"], "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {k: r[k] for k in r if k not in ("atoms_per_s", "ms_per_step", "gpu_launches")},
+            "gpu_launches": r["gpu_launches"]}))
 
 
 def train_epoch_probe(ncfg, dev, world=1):
@@ -379,8 +458,11 @@ def main():
                     help="supercell: configs[1], one independent 1M-atom cell per GPU (default, the contract "
                          "line); slab: configs[3]-style, ONE supercell of gpus x nx^3 cells split by spatial "
                          "domain with ghost halos (NCCL halo + reverse force exchange inside the step)")
-    ap.add_argument("--epoch-configs", type=int, default=1000,
+    ap.add_argument("--epoch-configs", type=int, default=20000,
                     help="size of the synthetic 64-atom-configuration set for the train_epoch probe (0 = off)")
+    ap.add_argument("--slab-cells", type=int, default=48,
+                    help="edge (conventional cells) of the ONE supercell of the slab probe, split over the ranks "
+                         "along a1 (0 = off); must be divisible by the number of GPUs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -511,7 +593,32 @@ def main():
         torch.cuda.synchronize()
         return packed
 
+    # ---- force contraction on the blocks of the last step (both directions), library events
+    scat = None
+    try:
+        image = torch.cat([torch.arange(n, dtype=torch.int32, device=dev), state["pi"]])
+        pack = dict(offsets=state["offsets"], indices=state["indices"], image=image, dz=state["dz"],
+                    dz_ptr=state["dz_ptr"], D=D, n_out=n)
+        w = torch.randn(n, D, dtype=torch.float64, device=dev)
+        F = ops._scatter_fwd(w, pack)
+        ops._scatter_bwd(F, pack)
+        torch.cuda.synchronize()
+        reps = 3
+        ops.kernel_timing(True)
+        for _ in range(reps):
+            flush.fill_(0)
+            F = ops._scatter_fwd(w, pack)
+        t_fwd = ops.kernel_timing(True)["scatter"][0] / reps
+        for _ in range(reps):
+            flush.fill_(0)
+            ops._scatter_bwd(F, pack)
+        t_bwd = ops.kernel_timing(False)["scatter"][0] / reps
+        scat = (t_fwd, t_bwd)
+        del w, F, pack, image
+    except Exception as e:
+        scat = e
     npad, pairs = int(state["npad"]), int(state["pairs"])
+    state_total = int(state["total"])
     state.clear()
     del timers
     torch.cuda.empty_cache()
@@ -535,6 +642,18 @@ def main():
         except Exception as e:  # reported, never required (single-process case only: see NCCL timeout)
             train_epoch = {"error": str(e)}
 
+    # one supercell split by spatial domain (strong scaling at a size that fits one GPU), all ranks
+    slab = None
+    if args.slab_cells > 0:
+        try:
+            del flush
+            torch.cuda.empty_cache()
+            slab = slab_probe(args.slab_cells, args.slab_cells, rank, world, dev, steps=max(3, min(args.steps, 5)))
+            if world == 8:  # BASELINE.json configs[3]: 10 M atoms over 8 GPUs
+                slab["config4_10M"] = slab_probe(8 * 54, 54, rank, world, dev, steps=3)
+        except Exception as e:
+            slab = {"error": f"{type(e).__name__}: {e}"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -555,6 +674,14 @@ def main():
     kinfo = {"launches_per_step": kern_n, "ms_per_step": kern_ms,
              "dominant": "symfun_sweep_kernel<true>",
              "note": "achieved = canonical work of one step / summed device time of these launches"}
+    traffic, traffic_src = ncu_traffic(args.nx)
+    fp64 = {"kernel": kname, "kernels": kinfo, "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": ach_tf / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": "DFMA-chain probe in this run (kb_probe_fp64_peak); B200 has no other FP64 unit: "
+                           "the FP64 mma.sync path shares this pipe (profiles/r01_probe_dmma_vs_dfma.txt)",
+            "note": "the BINDING roofline of the stage (SURVEY.md §8d: arithmetic intensity 10 flop/B > machine "
+                    "balance 5.6): canonical 380 618 flop/atom / summed device time of the stage's launches; "
+                    "traffic = DRAM bytes per step of those launches from the ncu capture named in traffic_source"}
     line = {
         "metric": "descriptor+dG/dr atoms/sec", "value": value, "unit": "atoms/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -566,45 +693,77 @@ def main():
                    "l2": "256 MiB write between timed steps (outside the step's CUDA events)",
                    "step_breakdown_ms": {"paddings+neighbors": float(np.mean(nl_ms)),
                                          "symfun+dG/dr": float(np.mean(sym_ms))}},
-        "roofline": {"kernel": kname, "kernels": kinfo, "bound": "hbm", "achieved": ach_gbs,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": (TRAFFIC_NCU_BYTES_PER_ATOM * n
-                                 if (args.nx == 50 and TRAFFIC_NCU_BYTES_PER_ATOM) else None),
-                     "traffic_source": "ncu capture profiles/r01_ncu_symfun_split_1M_traffic.txt (bytes per step: all launches of the stage)",
-                     "peak_source": peak_src,
-                     "note": "algorithmic bytes 36 724 B/atom; traffic adds the per-atom records handed from the "
-                             "table kernel to the sweep kernel (2 x 10.4 KB) and sector fills of the 24-byte row "
-                             "writes; the stage is bound by the FP64 and shared-memory pipes, see roofline_fp64"},
-        "roofline_fp64": {"kernel": kname, "bound": "fp64", "achieved": ach_tf,
-                          "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                          "peak_source": "DFMA-chain probe in this run (kb_probe_fp64_peak)",
-                          "note": "canonical 380 618 flop/atom (SURVEY.md §8d)"},
+        "roofline": fp64,
+        "roofline_fp64": {k: fp64[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "peak_source")},
+        "roofline_hbm": {"kernel": kname, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach_gbs / hbm_peak, "peak_source": peak_src,
+                         "note": "algorithmic bytes 36 724 B/atom (fp64 zeta + dG/dr written, inputs read once); "
+                                 "the non-binding term"},
         "e2e": {"value": e2e_value, "unit": "atoms/s", "h2d_bytes_per_step": int(24 * n),
                 "d2h_bytes_per_step": int(8 * n * D + 24 * n),
                 "what": "SymmetryFunction.transform_packed(Configuration with pinned host coords, "
                         "zeta_host=pinned array) + force contraction; zeta (streamed per 262 144-atom piece "
-                        "on a side stream) and forces copied back to pinned host memory"},
+                        "on a side stream) and forces copied back to pinned host memory; the dG/dr blocks "
+                        f"({8 * state_total / 1e9:.1f} GB) stay on the device: they are consumed there by the force "
+                        "contraction, the reference's dense equivalent would not fit any host"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if isinstance(scat, tuple):
+        line["roofline_scatter"] = {
+            "kernel": "force_scatter_kernel<false,double> (F = -sum dE/dG dG/dr) / force_gather_kernel<double> (adjoint)",
+            "bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "peak_source": peak_src,
+            "bytes_per_atom": BYTES_SCATTER,
+            "fwd": {"ms": scat[0], "achieved": BYTES_SCATTER * n / scat[0] / 1e6,
+                    "frac": BYTES_SCATTER * n / scat[0] / 1e6 / hbm_peak},
+            "bwd": {"ms": scat[1], "achieved": BYTES_SCATTER * n / scat[1] / 1e6,
+                    "frac": BYTES_SCATTER * n / scat[1] / 1e6 / hbm_peak},
+            "note": "library CUDA events around each launch, 256 MiB L2 flush between launches, on this step's blocks"}
+    elif scat is not None:
+        line["roofline_scatter"] = {"error": str(scat)}
+    if slab is not None:
+        line["slab"] = slab
     if train_epoch is not None:
         line["train_epoch"] = train_epoch
-    if cpu_base is not None:
+    if world == 1 and not args.no_cpu_baseline:
+        # (1) the reference package through its own driver (same call as --impl reference)
+        cores = len(os.sched_getaffinity(0))
+        try:
+            rate, text, _ = reference_descriptor_sample(cores, repeat=2)
+            line["cpu_baseline"] = {"value": rate, "unit": "atoms/s", "cores": cores, "kind": "reference",
+                                    "sample": text}
+        except Exception as e:  # the baseline is reported, never required
+            line["cpu_baseline"] = {"value": None, "unit": "atoms/s", "cores": 0, "kind": "reference",
+                                    "sample": f"failed: {str(e)[:200]}"}
+        # (2) its C++ alone (oracle/_ref shim, no Python scatter, no dense arrays): the faster CPU figure
         try:
             if isinstance(cpu_base, Exception):
                 raise cpu_base
             base = cpu_base
-            sample = int(max(2000, min(200000, 470.0 * base.cores * 12.0)))
+            sample = int(max(2000, min(200000, 470.0 * base.cores * 8.0)))
             base.run(base.cores * 8)
             rate = base.run(sample)
             base.close()
-            line["cpu_baseline"] = {
+            line["cpu_baseline_native"] = {
                 "value": rate, "unit": "atoms/s", "cores": base.cores, "kind": base.kind,
-                "sample": f"{sample} atoms of a {base.n}-atom jittered diamond cell (same lattice, cutoff, "
-                          f"set51), reference generate_one_atom(grad=True) over {base.cores} forked workers"}
-        except Exception as e:  # the baseline is reported, never required
-            line["cpu_baseline"] = {"value": None, "unit": "atoms/s", "cores": 0, "kind": "port",
-                                    "sample": f"failed: {e}"}
+                "sample": f"{sample} atoms of a {base.n}-atom jittered diamond cell (same lattice, cutoff, set51), "
+                          f"the reference's C++ generate_one_atom(grad=True) alone over {base.cores} forked workers "
+                          f"(serial paddings + neighbor list of the sample cell: {base.t_neigh:.2f} s, not included)"}
+        except Exception as e:
+            line["cpu_baseline_native"] = {"value": None, "sample": f"failed: {str(e)[:200]}"}
+        # (3) the reference's training epoch on CPU torch, beside train_epoch
+        if isinstance(train_epoch, dict) and "error" not in train_epoch:
+            try:
+                ep = ref_run("epoch", configs=200, nprocs=cores, epochs=1)
+                train_epoch["cpu_baseline"] = {
+                    "kind": "reference", "cores": cores, "configs": ep["configs"], "create_s": ep["create_s"],
+                    "epoch_s": ep["epoch_s"],
+                    "epoch_s_at_this_size": ep["epoch_s"] * train_epoch["configs"] / ep["configs"],
+                    "create_s_at_this_size": ep["create_s"] * train_epoch["configs"] / ep["configs"],
+                    "sample": f"{ep['configs']} of the same synthetic configurations: {ep['what']}; scaled linearly "
+                              f"in the number of configurations (both costs are per configuration)"}
+            except Exception as e:
+                train_epoch["cpu_baseline"] = {"error": str(e)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
