@@ -236,6 +236,50 @@ int64_t kb_launch_count(int32_t reset);
  * off.  Off by default: no events are created unless a caller (bench.py) asks. */
 int kb_kernel_timing(int32_t enable, double* h_ms, int32_t* h_launches);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Fused training step for small tanh MLPs over the packed fingerprints — replaces, for one     */
+/* batch, CalculatorTorch.compute (calculator_torch.py:161-228: model(zeta), autograd.grad with  */
+/* create_graph, the force contraction), Loss._get_loss_batch / energy_forces_residual            */
+/* (loss.py:37-110, 843-920), loss.backward() and torch.optim.Adam.step().                        */
+/* Network: x[n_in] -> (Linear(width[l]) -> tanh) x n_hidden -> Linear(1); parameters flat in     */
+/* torch order (W_1 [width_0][n_in] row-major, b_1, ..., W_out [1][width_last], b_out) in `dtype`. */
+/* ------------------------------------------------------------------------------------------ */
+#define KB_MLP_MAX_IN 128
+#define KB_MLP_MAX_HIDDEN 4
+#define KB_MLP_MAX_WIDTH 32
+typedef struct kb_mlp_desc
+{
+  int32_t n_in;
+  int32_t n_hidden;
+  int32_t width[KB_MLP_MAX_HIDDEN];
+  int32_t dtype;      /* KB_F32 / KB_F64: type of x, theta and of the optimizer moments */
+  int32_t reserved;
+} kb_mlp_desc;
+/* number of parameters and length (in `dtype` elements) of one atom's row of d_atom_vecs */
+int kb_mlp_num_params(const kb_mlp_desc* M, int32_t* n_params, int32_t* atom_vec);
+/* e_atom[n] (f64) and, when d_dEdx != NULL, dE/dx [n][n_in] (f64) */
+int kb_mlp_energy_grad(const kb_mlp_desc* M, int32_t n_atoms, const void* d_x, const void* d_theta,
+                       double* d_e_atom, double* d_dEdx, void* stream);
+/* Per configuration c of the batch (atoms [d_cfg_ptr[c] - atom0, d_cfg_ptr[c+1] - atom0) of the batch
+ * arrays): E_c = sum e_atom; r_e = w_e[c] (E_c - e_ref[c]); r_f = w_f[c] (F - f_ref) per component;
+ * *d_loss += (r_e^2 + sum r_f^2) * inv_nglobal; d_a[atom] = dL/de_atom; d_gF = dL/dF.
+ * w_e / w_f already hold config_weight * energy_weight (forces_weight) / natoms (loss.py:100-109). */
+int kb_train_residual(int32_t n_cfg, const int64_t* d_cfg_ptr, int64_t atom0, const double* d_e_atom,
+                      const double* d_forces, const double* d_e_ref, const double* d_f_ref,
+                      const double* d_w_e, const double* d_w_f, double inv_nglobal, int32_t use_energy,
+                      int32_t use_forces, double* d_a, double* d_gF, double* d_loss, void* stream);
+/* Parameter gradients d_grad[n_params] (f64) of L for a = dL/de_atom (d_a) and G = dL/d(dE/dx) (d_G, may
+ * be NULL: energy-only).  d_atom_vecs: scratch [n_atoms][atom_vec] in `dtype`; d_partials: scratch
+ * f64 [ceil(n_atoms / 64)][n_params].  Deterministic (no atomics). */
+int kb_mlp_param_grad(const kb_mlp_desc* M, int32_t n_atoms, const void* d_x, const void* d_theta,
+                      const double* d_a, const double* d_G, void* d_atom_vecs, double* d_partials,
+                      double* d_grad, void* stream);
+/* torch.optim.Adam's update (no amsgrad / weight decay) on the flat buffer, gradient = d_grad * grad_scale;
+ * *d_step (f64, device) is incremented: capturable in a CUDA graph. */
+int kb_adam_step(int32_t n_params, void* d_theta, const double* d_grad, double grad_scale, void* d_m,
+                 void* d_v, double* d_step, double lr, double beta1, double beta2, double eps,
+                 int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,14 @@ class kb_symfun_params(C.Structure):
     ]
 
 
+KB_MLP_MAX_IN, KB_MLP_MAX_HIDDEN, KB_MLP_MAX_WIDTH = 128, 4, 32
+
+
+class kb_mlp_desc(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("n_hidden", C.c_int32), ("width", C.c_int32 * KB_MLP_MAX_HIDDEN),
+                ("dtype", C.c_int32), ("reserved", C.c_int32)]
+
+
 # every symbol include/kliff_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "kb_version", "kb_error_string", "kb_device_info",
@@ -50,6 +58,7 @@ EXPORTS = [
     "kb_symfun_block_offsets", "kb_symfun_forward",
     "kb_force_scatter_fwd", "kb_force_scatter_bwd", "kb_dense_fold",
     "kb_probe_fp64_peak", "kb_probe_hbm_copy", "kb_launch_count", "kb_kernel_timing",
+    "kb_mlp_num_params", "kb_mlp_energy_grad", "kb_train_residual", "kb_mlp_param_grad", "kb_adam_step",
 ]
 
 _lib = None
@@ -105,6 +114,12 @@ def lib():
     L.kb_kernel_timing.argtypes = [i32, C.POINTER(dbl), C.POINTER(i32)]
     L.kb_launch_count.argtypes = [i32]
     L.kb_launch_count.restype = i64
+    md = C.POINTER(kb_mlp_desc)
+    L.kb_mlp_num_params.argtypes = [md, C.POINTER(i32), C.POINTER(i32)]
+    L.kb_mlp_energy_grad.argtypes = [md, i32, vp, vp, vp, vp, vp]
+    L.kb_train_residual.argtypes = [i32, vp, i64, vp, vp, vp, vp, vp, vp, dbl, i32, i32, vp, vp, vp, vp]
+    L.kb_mlp_param_grad.argtypes = [md, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.kb_adam_step.argtypes = [i32, vp, vp, dbl, vp, vp, vp, dbl, dbl, dbl, dbl, i32, vp]
     for name in EXPORTS:
         getattr(L, name)  # raises AttributeError when a declared symbol is missing
     _lib = L

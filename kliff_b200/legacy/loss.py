@@ -117,6 +117,11 @@ class LossNeuralNetworkModel:
         self._graphs = {}
         self._graph_pool = None
         self._graph_acc = None
+        # Fused training step (legacy/fused.py, csrc/train.cu): nine hand-written launches per batch on
+        # flat buffers, one CUDA graph per epoch.  Taken when the model is a small tanh MLP and the
+        # optimizer is plain Adam; `loss.use_fused = False` or KB_NO_FUSED=1 keeps the torch route.
+        self.use_fused = os.environ.get("KB_NO_FUSED", "0") != "1"
+        self._fused = None
 
     # ------------------------------------------------------------------ minimize (loss.py:740-828)
     def minimize(self, method="Adam", batch_size=100, num_epochs=1000, start_epoch=0, **kwargs):
@@ -138,12 +143,19 @@ class LossNeuralNetworkModel:
         chief = dist is None or dist.get_rank() == 0
         self.epoch_losses = []
         self._graphs, self._graph_pool, self._graph_acc = {}, None, None  # graphs belong to one optimizer
-        graphed = self._graphs_possible(method, kwargs) and self._prepare_graphs(method, kwargs)
+        self._fused = self._prepare_fused(method, kwargs)
+        graphed = (self._fused is None and self._graphs_possible(method, kwargs)
+                   and self._prepare_graphs(method, kwargs))
         epoch = 0
         for epoch in range(self.start_epoch, self.start_epoch + self.num_epochs):
             self._epoch = epoch
             if self.start_epoch != 0 and epoch == self.start_epoch:
                 epoch_loss = self._get_loss_epoch(loader)
+            elif self._fused is not None:
+                epoch_loss = self._fused.run_pass(self._fused_batches(), train=True,
+                                                  use_graph=self.use_cuda_graphs)
+                if chief:
+                    self.calculator.save_model(epoch)
             elif graphed:
                 epoch_loss = self._graphed_pass(train=True)
                 if chief:
@@ -287,7 +299,53 @@ class LossNeuralNetworkModel:
             self._graph_for(b, batch, train).replay()
         return float(self._graph_acc)
 
+    # ------------------------------------------------------------------ fused training step
+    def _prepare_fused(self, method, kwargs):
+        """FusedTrainer when this run is inside the fused kernels' domain, else None (torch route)."""
+        calc = self.calculator
+        if not (self.use_fused and self._fast_path() and method == "Adam" and type(calc) is CalculatorTorch):
+            return None
+        if calc.model.device.type != "cuda" or self.optimizer_state_path is not None:
+            return None
+        if set(kwargs) - {"lr", "betas", "eps", "weight_decay", "amsgrad"} or kwargs.get("weight_decay") \
+                or kwargs.get("amsgrad"):
+            return None
+        if not (calc.use_energy or calc.use_forces) or calc._packed.zeta_normalized is None:
+            return None
+        from .fused import FusedTrainer, mlp_structure
+        if mlp_structure(calc.model) is None:
+            return None
+        try:
+            return FusedTrainer(self, lr=kwargs.get("lr", 1e-3), betas=kwargs.get("betas", (0.9, 0.999)),
+                                eps=kwargs.get("eps", 1e-8))
+        except Exception as e:  # nothing has been touched yet: the torch route takes over
+            print(f"kliff_b200: fused training step disabled ({type(e).__name__}: {e})")
+            return None
+
+    def _fused_batches(self):
+        """This rank's (first, last + 1, global batch size) configuration run of every global batch."""
+        calc = self.calculator
+        bs = self.batch_size
+        shard = getattr(calc, "_shard", None)
+        out = []
+        if shard is not None:
+            r, w, n = shard
+            for lo in range(0, n, bs):
+                hi = min(lo + bs, n)
+                out.append((max(0, -((r - lo) // w)), max(0, -((r - hi) // w)), hi - lo))
+            return out
+        n = len(calc.fingerprints_dataset)
+        dist = _dist()
+        r, w = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+        for lo in range(0, n, bs):
+            hi = min(lo + bs, n)
+            m = hi - lo
+            out.append((lo + (m * r) // w, lo + (m * (r + 1)) // w, m))
+        return out
+
     def _get_loss_epoch(self, loader):
+        if self._fused is not None:
+            return self._fused.run_pass(self._fused_batches(), train=False, use_graph=self.use_cuda_graphs)
         if self._graph_acc is not None and self._graphs_live():
             return self._graphed_pass(train=False)
         total = 0.0
@@ -436,6 +494,9 @@ class LossNeuralNetworkModel:
 
     # ------------------------------------------------------------------ optimizer state (loss.py:922-935)
     def save_optimizer_state(self, path="optimizer_state.pkl"):
+        if self._fused is not None:  # flat Adam moments of the fused step (kliff_b200 format)
+            torch.save({"kliff_b200_fused_adam": self._fused.state_dict()}, path)
+            return
         torch.save(self.optimizer.state_dict(), path)
 
     def load_optimizer_state(self, path="optimizer_state.pkl"):

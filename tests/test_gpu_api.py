@@ -276,6 +276,61 @@ def test_published_loss_sequence_sic(workdir):
     assert os.path.exists("kliff_saved_model_si/model_Si_epoch7.pkl")
 
 
+@pytest.mark.parametrize("np_dtype,tol", [(np.float32, 2e-6), (np.float64, 1e-11)])
+def test_fused_training_step_matches_torch_route(workdir, np_dtype, tol):
+    """The hand-written fused step (csrc/train.cu behind Loss.minimize) against the torch route
+    (model(zeta), autograd.grad(create_graph), loss.backward(), torch.optim.Adam): same epoch losses and
+    same parameters after 3 epochs of 3 batches; and the gradient of one batch against autograd."""
+    weight = Weight(forces_weight=0.3)
+    confs = configs_from_npz("si_varying_alat.npz", weight=weight, limit=24)[:22]
+    runs = {}
+    for fused in (False, True):
+        desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": 5.0}, hyperparams="set51", normalize=True,
+                                dtype=np_dtype)
+        model = make_model(desc)
+        model.set_save_metadata(prefix=f"./m_{fused}", start=10 ** 6, frequency=10 ** 6)
+        calc = CalculatorTorch(model)
+        calc.create(confs, fingerprints_filename=f"fp_{fused}.pkl", fingerprints_mean_stdev_filename=f"ms_{fused}.pkl")
+        loss = Loss(calc)
+        loss.use_fused = fused
+        loss.minimize(method="Adam", num_epochs=3, batch_size=8, lr=0.005)
+        assert (loss._fused is not None) == fused
+        runs[fused] = (np.array(loss.epoch_losses), calc.get_opt_params().copy(), loss, calc)
+    a, b = runs[False], runs[True]
+    assert np.allclose(a[0], b[0], rtol=tol), (a[0], b[0])
+    assert np.allclose(a[1], b[1], rtol=50 * tol, atol=50 * tol * np.abs(a[1]).max())
+    # one batch, no optimizer: flat gradient of the fused kernels vs autograd on the torch route
+    loss_t, calc_t = a[2], a[3]
+    tr = b[2]._fused
+    calc_t.update_model_params(b[3].get_opt_params())
+    batch = calc_t.fingerprints_dataset.fp[3:11]
+    for p in calc_t.model.parameters():
+        p.grad = None
+    val = loss_t._get_loss_batch(batch)
+    val.backward()
+    g_ref = torch.cat([p.grad.reshape(-1) for p in calc_t.model.parameters()]).double().cpu().numpy()
+    tr.lr = 0.0  # the Adam kernel then leaves theta where it is
+    tr.acc.zero_()
+    tr.step(3, 11, 8, train=True)
+    g = tr.grad[:-1].cpu().numpy()
+    assert abs(float(tr.grad[-1]) - float(val)) <= tol * abs(float(val))
+    assert np.allclose(g, g_ref, rtol=0, atol=20 * tol * np.abs(g_ref).max())
+    # energy-only data takes the fused route without the force kernels
+    desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": 5.0}, hyperparams="set30", normalize=True,
+                            dtype=np_dtype)
+    outs = []
+    for fused in (False, True):
+        calc = CalculatorTorch(make_model(desc))
+        calc.model.set_save_metadata(prefix=f"./e_{fused}", start=10 ** 6, frequency=10 ** 6)
+        calc.create(confs[:6], use_forces=False, fingerprints_filename=f"fe_{fused}.pkl",
+                    fingerprints_mean_stdev_filename=f"me_{fused}.pkl")
+        loss = Loss(calc)
+        loss.use_fused = fused
+        loss.minimize(method="Adam", num_epochs=2, batch_size=4, lr=0.01)
+        outs.append(np.array(loss.epoch_losses))
+    assert np.allclose(outs[0], outs[1], rtol=tol)
+
+
 def test_custom_residual_function_route(workdir):
     """A user residual_fn forces the reference's per-configuration loop (loss.py:867-920)."""
     from kliff_b200.legacy.loss import energy_residual
