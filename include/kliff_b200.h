@@ -270,7 +270,7 @@ int kb_train_residual(int32_t n_cfg, const int64_t* d_cfg_ptr, int64_t atom0, co
                       int32_t use_forces, double* d_a, double* d_gF, double* d_loss, void* stream);
 /* Parameter gradients d_grad[n_params] (f64) of L for a = dL/de_atom (d_a) and G = dL/d(dE/dx) (d_G, may
  * be NULL: energy-only).  d_atom_vecs: scratch [n_atoms][atom_vec] in `dtype`; d_partials: scratch
- * f64 [ceil(n_atoms / 64)][n_params].  Deterministic (no atomics). */
+ * f64 [ceil(n_atoms / 32)][n_params].  Deterministic (no atomics). */
 int kb_mlp_param_grad(const kb_mlp_desc* M, int32_t n_atoms, const void* d_x, const void* d_theta,
                       const double* d_a, const double* d_G, void* d_atom_vecs, double* d_partials,
                       double* d_grad, void* stream);

@@ -72,11 +72,21 @@ __device__ __forceinline__ T forward_atom(const Net& N, const T* __restrict__ th
   {
     const T* W = th + N.w_off[l];
     const T* b = th + N.b_off[l];
-    for (int h = 0; h < N.H[l]; h++)
+    const int H = N.H[l];
+    for (int h = 0; h < H; h += 4)  // four units at a time: four independent chains per input load
     {
-      T z = b[h];
-      for (int d = 0; d < fan_in; d++) z = fma(W[h * fan_in + d], in[d], z);
-      act[l][h] = tanh_t<T>(z);
+      const int h1 = min(h + 1, H - 1), h2 = min(h + 2, H - 1), h3 = min(h + 3, H - 1);
+      T z0 = b[h], z1 = b[h1], z2 = b[h2], z3 = b[h3];
+      const T *w0 = W + h * fan_in, *w1 = W + h1 * fan_in, *w2 = W + h2 * fan_in, *w3 = W + h3 * fan_in;
+      for (int d = 0; d < fan_in; d++)
+      {
+        const T xd = in[d];
+        z0 = fma(w0[d], xd, z0); z1 = fma(w1[d], xd, z1); z2 = fma(w2[d], xd, z2); z3 = fma(w3[d], xd, z3);
+      }
+      act[l][h] = tanh_t<T>(z0);
+      if (h + 1 < H) act[l][h + 1] = tanh_t<T>(z1);
+      if (h + 2 < H) act[l][h + 2] = tanh_t<T>(z2);
+      if (h + 3 < H) act[l][h + 3] = tanh_t<T>(z3);
     }
     in = act[l];
     fan_in = N.H[l];
@@ -111,8 +121,9 @@ __device__ __forceinline__ void deltas_atom(const Net& N, const T* __restrict__ 
   }
 }
 
+constexpr int MLP_BLOCK = 64;  // small blocks: a 6 400-atom batch still covers 100 SMs
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MLP_BLOCK)
 mlp_energy_grad_kernel(const kb_mlp_desc M, int n, const T* __restrict__ x, const T* __restrict__ theta,
                        double* __restrict__ e_atom, double* __restrict__ dEdx)
 {
@@ -132,11 +143,21 @@ mlp_energy_grad_kernel(const kb_mlp_desc M, int n, const T* __restrict__ x, cons
   {
     deltas_atom<T>(N, th, act, u, delta);
     const T* W1 = th + N.w_off[0];
-    for (int d = 0; d < N.D; d++)
+    double* go = dEdx + (int64_t) t * N.D;
+    for (int d = 0; d < N.D; d += 4)
     {
-      T s = T(0);
-      for (int h = 0; h < N.H[0]; h++) s = fma(W1[h * N.D + d], delta[0][h], s);
-      dEdx[(int64_t) t * N.D + d] = (double) s;
+      const int d1 = min(d + 1, N.D - 1), d2 = min(d + 2, N.D - 1), d3 = min(d + 3, N.D - 1);
+      T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+      for (int h = 0; h < N.H[0]; h++)
+      {
+        const T dh = delta[0][h];
+        const T* w = W1 + h * N.D;
+        s0 = fma(w[d], dh, s0); s1 = fma(w[d1], dh, s1); s2 = fma(w[d2], dh, s2); s3 = fma(w[d3], dh, s3);
+      }
+      go[d] = (double) s0;
+      if (d + 1 < N.D) go[d + 1] = (double) s1;
+      if (d + 2 < N.D) go[d + 2] = (double) s2;
+      if (d + 3 < N.D) go[d + 3] = (double) s3;
     }
   }
 }
@@ -194,7 +215,7 @@ __host__ __device__ inline int atom_vec_len(const Net& N)
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MLP_BLOCK)
 mlp_backward_atoms_kernel(const kb_mlp_desc M, int n, const T* __restrict__ x, const T* __restrict__ theta,
                           const double* __restrict__ a_in, const double* __restrict__ G, T* __restrict__ V)
 {
@@ -216,11 +237,22 @@ mlp_backward_atoms_kernel(const kb_mlp_desc M, int n, const T* __restrict__ x, c
   if (G)
   {
     const T* W1 = th + N.w_off[0];
-    for (int h = 0; h < N.H[0]; h++)
+    const double* gr = G + (int64_t) t * N.D;
+    const int H = N.H[0];
+    for (int h = 0; h < H; h += 4)
     {
-      T s = T(0);
-      for (int d = 0; d < N.D; d++) s = fma(W1[h * N.D + d], (T) G[(int64_t) t * N.D + d], s);
-      Pv[h] = s;
+      const int h1 = min(h + 1, H - 1), h2 = min(h + 2, H - 1), h3 = min(h + 3, H - 1);
+      T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+      const T *w0 = W1 + h * N.D, *w1 = W1 + h1 * N.D, *w2 = W1 + h2 * N.D, *w3 = W1 + h3 * N.D;
+      for (int d = 0; d < N.D; d++)
+      {
+        const T gd = (T) gr[d];
+        s0 = fma(w0[d], gd, s0); s1 = fma(w1[d], gd, s1); s2 = fma(w2[d], gd, s2); s3 = fma(w3[d], gd, s3);
+      }
+      Pv[h] = s0;
+      if (h + 1 < H) Pv[h + 1] = s1;
+      if (h + 2 < H) Pv[h + 2] = s2;
+      if (h + 3 < H) Pv[h + 3] = s3;
     }
   }
   for (int l = 0; l < L; l++)
@@ -277,74 +309,93 @@ mlp_backward_atoms_kernel(const kb_mlp_desc M, int n, const T* __restrict__ x, c
   }
 }
 
-// Partial parameter gradients of a chunk of atoms: thread = parameter.
-constexpr int PG_CHUNK = 64;
+// Partial parameter gradients of a chunk of atoms: the chunk's per-atom vectors, inputs and G are staged
+// in shared memory (contiguous, coalesced copies), then thread = parameter sums over the chunk.
+constexpr int PG_CHUNK = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
 mlp_param_partials_kernel(const kb_mlp_desc M, int n, const T* __restrict__ x, const double* __restrict__ a_in,
                           const double* __restrict__ G, const T* __restrict__ V, double* __restrict__ partials)
 {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
   const Net N = make_net(M);
-  const int S = atom_vec_len(N);
-  const int lo = blockIdx.x * PG_CHUNK, hi = min(n, lo + PG_CHUNK);
+  const int S = atom_vec_len(N), D = N.D;
+  const int lo = blockIdx.x * PG_CHUNK, cnt = min(n, lo + PG_CHUNK) - lo;
+  T* sV = reinterpret_cast<T*>(sm_raw);        // [cnt][S]
+  T* sX = sV + PG_CHUNK * S;                   // [cnt][D]
+  T* sG = sX + PG_CHUNK * D;                   // [cnt][D]
+  T* sA = sG + PG_CHUNK * D;                   // [cnt]
+  T* sC = sA + PG_CHUNK;                       // {1, 0}
+  if (threadIdx.x == 0) { sC[0] = T(1); sC[1] = T(0); }
+  for (int q = threadIdx.x; q < cnt * S; q += blockDim.x) sV[q] = V[(int64_t) lo * S + q];
+  for (int q = threadIdx.x; q < cnt * D; q += blockDim.x)
+  {
+    sX[q] = x[(int64_t) lo * D + q];
+    sG[q] = G ? (T) G[(int64_t) lo * D + q] : T(0);
+  }
+  for (int q = threadIdx.x; q < cnt; q += blockDim.x) sA[q] = (T) a_in[lo + q];
+  __syncthreads();
   for (int p = threadIdx.x; p < N.P; p += blockDim.x)
   {
     // which parameter: layer (0..L = output), weight (i, j) or bias i
     int layer = 0;
     while (layer < N.L && p >= N.w_off[layer + 1]) layer++;
     const bool is_bias = p >= N.b_off[layer];
-    const int fan_in = layer == 0 ? N.D : N.H[layer - 1];
+    const int fan_in = layer == 0 ? D : N.H[layer - 1];
     const int q = is_bias ? p - N.b_off[layer] : p - N.w_off[layer];
     const int i = is_bias ? q : q / fan_in, j = is_bias ? 0 : q - i * fan_in;
-    int voff = 0;                                    // start of layer `layer`'s vectors inside an atom's V row
+    int voff = 0;                                    // start of layer `layer`'s vectors inside an atom's row
     for (int l = 0; l < layer && l < N.L; l++) voff += 4 * N.H[l];
     const int vprev = layer > 0 ? voff - 4 * N.H[layer - 1] : 0;  // previous hidden layer's vectors
-    double acc = 0.0;
-    for (int t = lo; t < hi; t++)
+    // every case is sum_t A[t] * B[t] + C[t] * E[t] over rows of the staged arrays
+    const T *pa, *pb, *pc, *pe;
+    int sa, sb, sc, se;
+    const T *one = sC, *zero = sC + 1;
+    if (layer < N.L)
     {
-      const T* v = V + (int64_t) t * S;
-      if (layer < N.L)
+      const int H = N.H[layer];
+      pa = sV + voff + i; sa = S;                                        // Q_l[i]
+      if (is_bias) { pb = one; sb = 0; pc = zero; sc = 0; pe = zero; se = 0; }
+      else if (layer == 0)
       {
-        const int H = N.H[layer];
-        const T Qi = v[voff + i];
-        if (is_bias) acc += (double) Qi;
-        else if (layer == 0)
-        {
-          T c = Qi * x[(int64_t) t * N.D + j];
-          if (G) c = fma(v[voff + H + i], (T) G[(int64_t) t * N.D + j], c);   // delta_1 G^T
-          acc += (double) c;
-        }
-        else
-        {
-          const int Hp = N.H[layer - 1];
-          T c = Qi * v[vprev + 3 * Hp + j];                                    // Q_l a_{l-1}^T
-          c = fma(v[voff + H + i], v[vprev + 2 * Hp + j], c);                  // delta_l R_{l-1}^T
-          acc += (double) c;
-        }
+        pb = sX + j; sb = D;                                             // x[j]
+        pc = sV + voff + H + i; sc = S; pe = sG + j; se = D;             // delta_1[i] G[j]
       }
       else
       {
-        const T a = (T) a_in[t];
-        if (is_bias) acc += (double) a;
-        else
-        {
-          const int Hp = N.H[N.L - 1];
-          acc += (double) fma(a, v[vprev + 3 * Hp + j], v[vprev + 2 * Hp + j]);  // a a_L + R_L
-        }
+        const int Hp = N.H[layer - 1];
+        pb = sV + vprev + 3 * Hp + j; sb = S;                            // a_{l-1}[j]
+        pc = sV + voff + H + i; sc = S; pe = sV + vprev + 2 * Hp + j; se = S;  // delta_l[i] R_{l-1}[j]
       }
     }
+    else
+    {
+      pa = sA; sa = 1;                                                   // a
+      if (is_bias) { pb = one; sb = 0; pc = zero; sc = 0; pe = zero; se = 0; }
+      else
+      {
+        const int Hp = N.H[N.L - 1];
+        pb = sV + vprev + 3 * Hp + j; sb = S;                            // a_L[j]
+        pc = one; sc = 0; pe = sV + vprev + 2 * Hp + j; se = S;          // + R_L[j]
+      }
+    }
+    double acc = 0.0;
+    for (int t = 0; t < cnt; t++)
+      acc += (double) fma(pa[t * sa], pb[t * sb], pc[t * sc] * pe[t * se]);
     partials[(int64_t) blockIdx.x * N.P + p] = acc;
   }
 }
 
-__global__ void reduce_partials_kernel(int n_chunks, int P, const double* __restrict__ partials,
-                                       double* __restrict__ grad)
+// grad[p] = sum over chunks, one warp per parameter, fixed order (deterministic)
+__global__ void __launch_bounds__(128)
+reduce_partials_kernel(int n_chunks, int P, const double* __restrict__ partials, double* __restrict__ grad)
 {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (p >= P) return;
   double s = 0.0;
-  for (int c = 0; c < n_chunks; c++) s += partials[(int64_t) c * P + p];
-  grad[p] = s;
+  for (int c = lane; c < n_chunks; c += 32) s += partials[(int64_t) c * P + p];
+  s = warp_sum(s);
+  if (lane == 0) grad[p] = s;
 }
 
 // torch.optim.Adam (no amsgrad, no weight decay), torch/optim/adam.py `_single_tensor_adam`:
@@ -404,12 +455,12 @@ extern "C" int kb_mlp_energy_grad(const kb_mlp_desc* M, int32_t n_atoms, const v
   if (n_atoms < 0 || !d_x || !d_theta || !d_e_atom) return KB_ERR_INVALID;
   if (n_atoms == 0) return KB_OK;
   const Net N = make_net(*M);
-  const int nb = (n_atoms + 127) / 128;
+  const int nb = (n_atoms + MLP_BLOCK - 1) / MLP_BLOCK;
   if (M->dtype == KB_F32)
-    mlp_energy_grad_kernel<float><<<nb, 128, sizeof(float) * N.P, kb_stream(stream)>>>(
+    mlp_energy_grad_kernel<float><<<nb, MLP_BLOCK, sizeof(float) * N.P, kb_stream(stream)>>>(
         *M, n_atoms, static_cast<const float*>(d_x), static_cast<const float*>(d_theta), d_e_atom, d_dEdx);
   else
-    mlp_energy_grad_kernel<double><<<nb, 128, sizeof(double) * N.P, kb_stream(stream)>>>(
+    mlp_energy_grad_kernel<double><<<nb, MLP_BLOCK, sizeof(double) * N.P, kb_stream(stream)>>>(
         *M, n_atoms, static_cast<const double*>(d_x), static_cast<const double*>(d_theta), d_e_atom, d_dEdx);
   KB_LAUNCH_CHECK();
   return KB_OK;
@@ -445,25 +496,28 @@ extern "C" int kb_mlp_param_grad(const kb_mlp_desc* M, int32_t n_atoms, const vo
     KB_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(double) * N.P, st));
     return KB_OK;
   }
-  const int nb = (n_atoms + 127) / 128;
+  const int nb = (n_atoms + MLP_BLOCK - 1) / MLP_BLOCK;
   const int nc = (n_atoms + PG_CHUNK - 1) / PG_CHUNK;
+  const size_t pg_smem = (size_t) PG_CHUNK * (atom_vec_len(N) + 2 * N.D + 1) + 2;  // elements
   if (M->dtype == KB_F32)
   {
-    mlp_backward_atoms_kernel<float><<<nb, 128, sizeof(float) * N.P, st>>>(
+    mlp_backward_atoms_kernel<float><<<nb, MLP_BLOCK, sizeof(float) * N.P, st>>>(
         *M, n_atoms, static_cast<const float*>(d_x), static_cast<const float*>(d_theta), d_a, d_G,
         static_cast<float*>(d_atom_vecs));
-    mlp_param_partials_kernel<float><<<nc, 256, 0, st>>>(*M, n_atoms, static_cast<const float*>(d_x), d_a, d_G,
-                                                         static_cast<const float*>(d_atom_vecs), d_partials);
+    mlp_param_partials_kernel<float><<<nc, 256, pg_smem * sizeof(float), st>>>(
+        *M, n_atoms, static_cast<const float*>(d_x), d_a, d_G, static_cast<const float*>(d_atom_vecs), d_partials);
   }
   else
   {
-    mlp_backward_atoms_kernel<double><<<nb, 128, sizeof(double) * N.P, st>>>(
+    mlp_backward_atoms_kernel<double><<<nb, MLP_BLOCK, sizeof(double) * N.P, st>>>(
         *M, n_atoms, static_cast<const double*>(d_x), static_cast<const double*>(d_theta), d_a, d_G,
         static_cast<double*>(d_atom_vecs));
-    mlp_param_partials_kernel<double><<<nc, 256, 0, st>>>(*M, n_atoms, static_cast<const double*>(d_x), d_a, d_G,
-                                                          static_cast<const double*>(d_atom_vecs), d_partials);
+    cudaFuncSetAttribute(mlp_param_partials_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int) (pg_smem * sizeof(double)));
+    mlp_param_partials_kernel<double><<<nc, 256, pg_smem * sizeof(double), st>>>(
+        *M, n_atoms, static_cast<const double*>(d_x), d_a, d_G, static_cast<const double*>(d_atom_vecs), d_partials);
   }
-  reduce_partials_kernel<<<(N.P + 127) / 128, 128, 0, st>>>(nc, N.P, d_partials, d_grad);
+  reduce_partials_kernel<<<(N.P + 3) / 4, 128, 0, st>>>(nc, N.P, d_partials, d_grad);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return -(int) e;
   kb_note_launch(3);

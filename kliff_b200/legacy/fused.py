@@ -142,7 +142,7 @@ class FusedTrainer:
         self.gF = torch.empty(3 * n, dtype=torch.float64, device=dev)
         self.G = torch.empty((n, D), dtype=torch.float64, device=dev)
         self.avecs = torch.empty((n, self.net.avec), dtype=self.net.dt, device=dev)
-        self.partials = torch.empty(((n + 63) // 64, self.net.P), dtype=torch.float64, device=dev)
+        self.partials = torch.empty(((n + 31) // 32, self.net.P), dtype=torch.float64, device=dev)
         self._sized = n
 
     # ------------------------------------------------------------------------------------------
