@@ -324,12 +324,15 @@ def slab_probe(nx_total, ny, rank, world, dev, steps, warmup=3):
         del fp
     barrier()
     launches = ops.launch_count() - launches0
-    tot = torch.tensor([sum(ms), float(n_own), float(F.sum(dim=0).abs().max())], dtype=torch.float64, device=dev)
+    net = F.sum(dim=0)                          # total force on the cell: zero by translation invariance
+    tot = torch.tensor([sum(ms), float(n_own), 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
+    tot[2:5] = net
     tmax = tot.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     total_ms, atoms = float(tmax[0]), float(tot[1])
+    tot[2] = tot[2:5].abs().max()
     del flush, w, x_own
     torch.cuda.empty_cache()
     return {"workload": f"ONE diamond-Si supercell of {nx_total}x{ny}x{ny} cells, slab of {nxs} cells per GPU, "
@@ -524,7 +527,9 @@ def main():
     if args.workload == "slab":
         run_slab_workload(args, rank, world, dev)
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+        leave(world)
         return
 
     # ---- synthetic input, resident in HBM before the timed region
@@ -676,9 +681,11 @@ def main():
         except Exception as e:
             slab = {"error": f"{type(e).__name__}: {e}"}
 
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave(world)
         return
 
     hbm_peak, peak_src = measured_peaks()
@@ -787,8 +794,18 @@ def main():
             except Exception as e:
                 train_epoch["cpu_baseline"] = {"error": str(e)[:200]}
     print(json.dumps(line))
+    leave(world)
+
+
+def leave(world):
+    """End of a rank.  Multi-rank runs leave without dist.destroy_process_group(): CUDA graphs that
+    captured NCCL collectives are still alive at this point and tearing the communicator down under them
+    was seen to block; every collective has completed (barrier + synchronize above), so the process
+    simply exits."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":
