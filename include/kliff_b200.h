@@ -237,6 +237,19 @@ int64_t kb_launch_count(int32_t reset);
 int kb_kernel_timing(int32_t enable, double* h_ms, int32_t* h_launches);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Column statistics and normalisation of the descriptor matrix — replaces np.mean / np.std and  */
+/* (zeta - mean) / stdev of Descriptor.generate_fingerprints                                     */
+/* (kliff/legacy/descriptors/descriptor.py:116-118, 187-194).  Deterministic two-stage sums.      */
+/* kb_moments: d_out[d] = sum_r zeta[r][d] when d_mean == NULL, else sum_r (zeta[r][d] - mean[d])^2 */
+/* (numpy's two-pass definition: the caller divides by the row count, all-reduces across ranks).  */
+/* kb_normalize: d_out[r][d] = (zeta[r][d] - mean[d]) * inv_stdev[d]  (d_out may alias d_zeta).    */
+/* ------------------------------------------------------------------------------------------ */
+int kb_moments(int64_t n_rows, int32_t n_desc, const double* d_zeta, const double* d_mean,
+               double* d_out, void* stream);
+int kb_normalize(int64_t n_rows, int32_t n_desc, const double* d_zeta, const double* d_mean,
+                 const double* d_inv_stdev, double* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Fused training step for small tanh MLPs over the packed fingerprints — replaces, for one     */
 /* batch, CalculatorTorch.compute (calculator_torch.py:161-228: model(zeta), autograd.grad with  */
 /* create_graph, the force contraction), Loss._get_loss_batch / energy_forces_residual            */

@@ -58,6 +58,7 @@ EXPORTS = [
     "kb_symfun_block_offsets", "kb_symfun_forward",
     "kb_force_scatter_fwd", "kb_force_scatter_bwd", "kb_dense_fold",
     "kb_probe_fp64_peak", "kb_probe_hbm_copy", "kb_launch_count", "kb_kernel_timing",
+    "kb_moments", "kb_normalize",
     "kb_mlp_num_params", "kb_mlp_energy_grad", "kb_train_residual", "kb_mlp_param_grad", "kb_adam_step",
 ]
 
@@ -114,6 +115,8 @@ def lib():
     L.kb_kernel_timing.argtypes = [i32, C.POINTER(dbl), C.POINTER(i32)]
     L.kb_launch_count.argtypes = [i32]
     L.kb_launch_count.restype = i64
+    L.kb_moments.argtypes = [i64, i32, vp, vp, vp, vp]
+    L.kb_normalize.argtypes = [i64, i32, vp, vp, vp, vp, vp]
     md = C.POINTER(kb_mlp_desc)
     L.kb_mlp_num_params.argtypes = [md, C.POINTER(i32), C.POINTER(i32)]
     L.kb_mlp_energy_grad.argtypes = [md, i32, vp, vp, vp, vp, vp]

@@ -75,15 +75,22 @@ extern "C" int kb_symfun_block_offsets(int32_t n_centers, const int32_t* d_cente
   }
   int64_t* sizes = nullptr;
   KB_CUDA(cudaMallocAsync((void**) &sizes, sizeof(int64_t) * (size_t) n_centers, st));
+  int rc = KB_OK;
   block_size_kernel<<<(n_centers + 255) / 256, 256, 0, st>>>(n_centers, d_centers, d_nl_offsets,
                                                              n_desc, sizes);
-  KB_LAUNCH_CHECK();
-  int rc = kb_exclusive_scan<int64_t, int64_t>(sizes, d_dz_ptr, n_centers, d_dz_ptr + n_centers, st);
-  if (rc) return rc;
-  KB_CUDA(cudaMemcpyAsync(h_total, d_dz_ptr + n_centers, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  KB_CUDA(cudaFreeAsync(sizes, st));
-  KB_CUDA(cudaStreamSynchronize(st));
-  return KB_OK;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) rc = -(int) e;
+  else kb_note_launch();
+  if (rc == KB_OK) rc = kb_exclusive_scan<int64_t, int64_t>(sizes, d_dz_ptr, n_centers, d_dz_ptr + n_centers, st);
+  if (rc == KB_OK)
+  {
+    e = cudaMemcpyAsync(h_total, d_dz_ptr + n_centers, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = -(int) e;
+  }
+  cudaFreeAsync(sizes, st);  // on every path
+  e = cudaStreamSynchronize(st);
+  if (rc == KB_OK && e != cudaSuccess) rc = -(int) e;
+  return rc;
 }
 
 extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_centers,
@@ -113,8 +120,11 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
   {
     int32_t* ov = nullptr;
     KB_CUDA(cudaMallocAsync((void**) &ov, sizeof(int32_t) * ((size_t) n_centers + 2), st));
-    KB_CUDA(cudaMemsetAsync(ov, 0, 2 * sizeof(int32_t), st));
     bool launched = false, may_overflow = false;
+    {
+      cudaError_t e0 = cudaMemsetAsync(ov, 0, 2 * sizeof(int32_t), st);
+      if (e0 != cudaSuccess) { cudaFreeAsync(ov, st); return -(int) e0; }
+    }
     if (mode == KB_SYMFUN_WARP)
       rc = kb_symfun_warp_launch(P, n_centers, d_centers, nullptr, d_coords, d_species, d_nl_offsets,
                                  d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov, 0, &launched,
@@ -133,8 +143,14 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
       {
         // second pass with worst-case record capacity over the declined atoms only
         int32_t* ov2 = nullptr;
-        KB_CUDA(cudaMallocAsync((void**) &ov2, sizeof(int32_t) * ((size_t) n_over + 2), st));
-        KB_CUDA(cudaMemsetAsync(ov2, 0, 2 * sizeof(int32_t), st));
+        e = cudaMallocAsync((void**) &ov2, sizeof(int32_t) * ((size_t) n_over + 2), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ov2, 0, 2 * sizeof(int32_t), st);
+        if (e != cudaSuccess)
+        {
+          if (ov2) cudaFreeAsync(ov2, st);
+          cudaFreeAsync(ov, st);
+          return -(int) e;
+        }
         bool l2 = false, m2 = false;
         rc = kb_symfun_warp_launch(P, n_over, d_centers, ov + 2, d_coords, d_species, d_nl_offsets,
                                    d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov2, 1, &l2, &m2, st);
@@ -159,7 +175,10 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
   // ---- CTA-per-atom kernel: g5 families and generic exponents
   int32_t* d_overflow = nullptr;
   KB_CUDA(cudaMallocAsync((void**) &d_overflow, sizeof(int32_t) * ((size_t) n_centers + 1), st));
-  KB_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), st));
+  {
+    cudaError_t e0 = cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), st);
+    if (e0 != cudaSuccess) { cudaFreeAsync(d_overflow, st); return -(int) e0; }
+  }
   bool may_overflow = false;
   rc = kb_symfun_tiled_launch(P, n_centers, d_centers, d_coords, d_species, d_nl_offsets,
                               d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, d_overflow,

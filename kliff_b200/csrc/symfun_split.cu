@@ -222,9 +222,17 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
   const int n_chunks = (n_centers + chunk - 1) / chunk;
   unsigned char* records = nullptr;
   int32_t* work = nullptr;
-  KB_CUDA(cudaMallocAsync((void**) &records, (size_t) chunk * L.bytes, st));
-  KB_CUDA(cudaMallocAsync((void**) &work, sizeof(int32_t) * (size_t) n_chunks, st));
-  KB_CUDA(cudaMemsetAsync(work, 0, sizeof(int32_t) * (size_t) n_chunks, st));
+  {
+    cudaError_t e = cudaMallocAsync((void**) &records, (size_t) chunk * L.bytes, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**) &work, sizeof(int32_t) * (size_t) n_chunks, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(work, 0, sizeof(int32_t) * (size_t) n_chunks, st);
+    if (e != cudaSuccess)
+    {
+      if (records) cudaFreeAsync(records, st);
+      if (work) cudaFreeAsync(work, st);
+      return -(int) e;
+    }
+  }
 
   SplitArgs A;
   A.centers = d_centers; A.subset = d_subset; A.coords = d_coords; A.species = d_species;

@@ -42,10 +42,34 @@ def _rank_suffix(filename, rank):
 
 
 def _get_device(gpu):
-    """calculator_torch.py:582-594, minus the CPU branch."""
+    """calculator_torch.py:582-594, minus the CPU branch: `gpu=False` / `None` in the reference mean
+    "run on the CPU"; this package has no CPU path, so they select the current CUDA device (said once)."""
     if gpu is None or isinstance(gpu, bool):
+        if gpu is False and not _get_device.warned:
+            _get_device.warned = True
+            import warnings
+            warnings.warn("kliff_b200 has no CPU path: CalculatorTorch(gpu=False) runs on the current CUDA "
+                          "device", stacklevel=3)
         return default_device()
     return torch.device("cuda", int(gpu))
+
+
+_get_device.warned = False
+
+
+def _on_model_device(method):
+    """Run a calculator method with the model's device as the current CUDA device, so that every
+    library call (streams, scratch, default_device()) lands on the device `gpu=<index>` selected."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        dev = self.model.device
+        if dev.type != "cuda" or dev.index is None or dev.index == torch.cuda.current_device():
+            return method(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return method(self, *args, **kwargs)
+    return wrapper
 
 
 def _runs(indices):
@@ -81,6 +105,7 @@ class CalculatorTorch:
         self._shard = None
 
     # ------------------------------------------------------------------ create (:41-126)
+    @_on_model_device
     def create(self, configs, use_energy=True, use_forces=True, use_stress=False,
                fingerprints_filename="fingerprints.pkl", fingerprints_mean_stdev_filename=None,
                reuse=False, use_welford_method=False, nprocs=1, shard_configs=None):
@@ -109,6 +134,18 @@ class CalculatorTorch:
                 fingerprints_mean_stdev_filename = _rank_suffix(fingerprints_mean_stdev_filename, r)
         if reuse:
             self.fingerprints_path = to_path(fingerprints_filename)
+            if dist is not None and (shard_configs is None or shard_configs):
+                # files of an earlier sharded create(): every rank reads its own share back
+                r, w = dist.get_rank(), dist.get_world_size()
+                mine = _rank_suffix(fingerprints_filename, r)
+                if mine.exists():
+                    self.fingerprints_path = mine
+                    self._shard = (r, w, len(configs))
+                    ms = fingerprints_mean_stdev_filename or "fingerprints_mean_and_stdev.pkl"
+                    if r != 0 and _rank_suffix(ms, r).exists():
+                        fingerprints_mean_stdev_filename = _rank_suffix(ms, r)
+                    elif fingerprints_mean_stdev_filename is None and to_path(ms).exists():
+                        fingerprints_mean_stdev_filename = ms
             if not self.fingerprints_path.exists():
                 raise CalculatorTorchError(
                     f"You specified `reuse=True` to reuse the fingerprints stored in "
@@ -200,6 +237,7 @@ class CalculatorTorch:
                 return False
         return True
 
+    @_on_model_device
     def compute_packed(self, cfg_indices, want_forces=None):
         """Vectorised core: energies [B] and flat forces [3 * atoms in batch] (both in the model
         dtype, differentiable w.r.t. the model parameters) for configurations `cfg_indices`,
@@ -236,6 +274,7 @@ class CalculatorTorch:
             forces = (pieces[0] if len(pieces) == 1 else torch.cat(pieces)).to(dt)
         return energy, forces, natoms
 
+    @_on_model_device
     def compute(self, batch):
         grad = self.use_forces or self.use_stress
         if self._packed_usable(batch) and not self.use_stress:

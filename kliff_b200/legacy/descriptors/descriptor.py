@@ -13,6 +13,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
+from ... import ops
 from ...utils import create_directory, pickle_dump, to_path
 
 
@@ -68,18 +69,17 @@ class Descriptor:
 
         has_mean_stdev = self.mean is not None and self.stdev is not None
         if self.normalize and not has_mean_stdev:
+            # np.mean / np.std (ddof = 0) in their two-pass form, as device reductions (kb_moments);
+            # over all ranks' atoms when the set is sharded
             z = packed.zeta
-            if reduce_over is None:
-                mean = z.mean(dim=0)
-                stdev = torch.sqrt(((z - mean) ** 2).mean(dim=0))  # np.std, ddof = 0
-            else:
-                # same two-pass definition over all ranks' atoms: sum -> mean, then sum of squares
-                first = torch.cat([z.sum(dim=0), torch.tensor([float(z.shape[0])], dtype=z.dtype, device=z.device)])
+            first = torch.cat([ops.moments(z), torch.tensor([float(z.shape[0])], dtype=z.dtype, device=z.device)])
+            if reduce_over is not None:
                 reduce_over.all_reduce(first, op=reduce_over.ReduceOp.SUM)
-                mean = first[:-1] / first[-1]
-                second = ((z - mean) ** 2).sum(dim=0)
+            mean = first[:-1] / first[-1]
+            second = ops.moments(z, mean)
+            if reduce_over is not None:
                 reduce_over.all_reduce(second, op=reduce_over.ReduceOp.SUM)
-                stdev = torch.sqrt(second / first[-1])
+            stdev = torch.sqrt(second / first[-1])
             self.mean = mean.cpu().numpy()
             self.stdev = stdev.cpu().numpy()
             if fingerprints_mean_stdev_filename is None:
@@ -89,7 +89,7 @@ class Descriptor:
         if self.normalize:
             mean_d = torch.as_tensor(self.mean, device=packed.device, dtype=torch.float64)
             inv_d = 1.0 / torch.as_tensor(self.stdev, device=packed.device, dtype=torch.float64)
-            packed.zeta_normalized = (packed.zeta - mean_d) * inv_d
+            packed.zeta_normalized = ops.normalize(packed.zeta, mean_d, inv_d)
             packed.scale = inv_d.contiguous()
         else:
             packed.zeta_normalized = packed.zeta

@@ -125,6 +125,10 @@ class LossNeuralNetworkModel:
 
     # ------------------------------------------------------------------ minimize (loss.py:740-828)
     def minimize(self, method="Adam", batch_size=100, num_epochs=1000, start_epoch=0, **kwargs):
+        dev = self.calculator.model.device
+        if dev.type == "cuda" and dev.index is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):  # CalculatorTorch(model, gpu=<index>): everything on that device
+                return self.minimize(method, batch_size, num_epochs, start_epoch, **kwargs)
         if method not in self.torch_minimize_methods:
             raise LossError(f"Minimization method `{method}` not supported.")
         self.batch_size, self.num_epochs, self.start_epoch = batch_size, num_epochs, start_epoch

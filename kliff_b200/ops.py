@@ -346,6 +346,27 @@ def dense_fold(pack, coords, n_contrib, want_forces=True, want_stress=False):
     return dense, stress
 
 
+def moments(zeta, mean=None):
+    """Column sums of zeta [n, D] (mean=None) or of (zeta - mean)^2: the two passes of np.mean / np.std
+    (descriptor.py:116-118) as deterministic device reductions.  Returns f64 [D]."""
+    _need_cuda(zeta)
+    zeta = zeta.contiguous()
+    out = torch.empty(zeta.shape[1], dtype=torch.float64, device=zeta.device)
+    check(_lib.lib().kb_moments(zeta.shape[0], zeta.shape[1], _ptr(zeta), _ptr(mean), _ptr(out), _stream()),
+          "kb_moments")
+    return out
+
+
+def normalize(zeta, mean, inv_stdev, out=None):
+    """(zeta - mean) * inv_stdev (descriptor.py:187-194)."""
+    _need_cuda(zeta, mean, inv_stdev)
+    zeta = zeta.contiguous()
+    out = torch.empty_like(zeta) if out is None else out
+    check(_lib.lib().kb_normalize(zeta.shape[0], zeta.shape[1], _ptr(zeta), _ptr(mean.contiguous()),
+                                  _ptr(inv_stdev.contiguous()), _ptr(out), _stream()), "kb_normalize")
+    return out
+
+
 def probe_fp64_peak():
     v = C.c_double(0.0)
     check(_lib.lib().kb_probe_fp64_peak(C.byref(v), _stream()), "kb_probe_fp64_peak")

@@ -614,3 +614,28 @@ def test_streamed_host_descriptors_equal_single_pass(dev):
     q.host_ready.synchronize()
     # (the value-only pass runs the round-1 sweep: same sums in another order)
     assert torch.allclose(host, ref.zeta.cpu(), rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.parametrize("n,D", [(0, 51), (1, 51), (513, 30), (70001, 51)])
+def test_moments_and_normalize_vs_numpy(dev, n, D):
+    """kb_moments / kb_normalize against np.mean / np.std / (zeta - mean) / stdev
+    (kliff/legacy/descriptors/descriptor.py:116-118, 187-194): <= 1e-13 relative, and two runs
+    bit-identical (deterministic two-stage sums)."""
+    rng = np.random.default_rng(n + D)
+    z = rng.normal(3.0, 2.0, size=(n, D)) * rng.uniform(0.1, 50.0, size=D)
+    zd = torch.as_tensor(z, device=dev)
+    s1 = ops.moments(zd)
+    assert torch.equal(s1, ops.moments(zd))
+    if n == 0:
+        assert float(s1.abs().max()) == 0.0
+        return
+    mean = s1 / n
+    assert np.allclose(mean.cpu().numpy(), z.mean(axis=0), rtol=1e-13, atol=0)
+    s2 = ops.moments(zd, mean)
+    assert torch.equal(s2, ops.moments(zd, mean))
+    std = torch.sqrt(s2 / n)
+    assert np.allclose(std.cpu().numpy(), z.std(axis=0), rtol=1e-12, atol=1e-300)
+    if n > 1:
+        out = ops.normalize(zd, mean, 1.0 / std)
+        want = (z - z.mean(axis=0)) / z.std(axis=0)
+        assert np.allclose(out.cpu().numpy(), want, rtol=1e-11, atol=1e-11)
