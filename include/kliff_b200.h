@@ -230,10 +230,12 @@ int kb_probe_hbm_copy(size_t bytes, double* h_gbs, void* stream);
 /* Number of kernels this library has launched in this process (reset != 0 zeroes it). */
 int64_t kb_launch_count(int32_t reset);
 /* Per-kernel device times of the descriptor stage, measured with CUDA events on the launching
- * stream.  Returns in h_ms[4] / h_launches[4] (either may be NULL) the summed duration and number
+ * stream.  Returns in h_ms[5] / h_launches[5] (either may be NULL) the summed duration and number
  * of launches recorded since the previous call, by kernel: [0] symfun_prep_kernel, [1]
- * symfun_sweep_kernel / symfun_qsweep_kernel, [2] fused symfun_warp_kernel, [3] force_scatter / force_gather kernels; then switches recording on (enable != 0) or
- * off.  Off by default: no events are created unless a caller (bench.py) asks. */
+ * symfun_sweep3_kernel / symfun_sweep_kernel / symfun_qsweep_kernel, [2] fused symfun_warp_kernel,
+ * [3] force_scatter / force_gather kernels, [4] the whole two-stage descriptor path of a call (all its
+ * chunks, table kernel + sweep); then switches recording on (enable != 0) or off.  Off by default: no events
+ * are created unless a caller (bench.py) asks. */
 int kb_kernel_timing(int32_t enable, double* h_ms, int32_t* h_launches);
 
 /* ------------------------------------------------------------------------------------------ */

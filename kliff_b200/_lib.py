@@ -17,6 +17,8 @@ KB_SYMFUN_AUTO, KB_SYMFUN_GENERAL, KB_SYMFUN_TILED, KB_SYMFUN_WARP, KB_SYMFUN_SP
 KB_F64, KB_F32 = 0, 1
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libkliff_b200.so")
+if os.environ.get("KB_LIB_PATH"):  # tuning aid: a differently compiled build of the same library
+    LIB_PATH = os.environ["KB_LIB_PATH"]
 
 
 class kb_symfun_params(C.Structure):

@@ -27,7 +27,7 @@ void kb_note_launch(int n = 1);
 
 // Optional per-kernel timing (kb_kernel_timing): when switched on, launch sites bracket their kernel
 // with CUDA events on the launching stream under a small integer tag.  Off by default (no events).
-enum { KB_T_PREP = 0, KB_T_SWEEP = 1, KB_T_FUSED = 2, KB_T_SCATTER = 3, KB_T_COUNT = 4 };
+enum { KB_T_PREP = 0, KB_T_SWEEP = 1, KB_T_FUSED = 2, KB_T_SCATTER = 3, KB_T_STAGE = 4, KB_T_COUNT = 5 };
 bool kb_timing_on();
 void kb_timing_begin(int tag, cudaStream_t st);
 void kb_timing_end(int tag, cudaStream_t st);

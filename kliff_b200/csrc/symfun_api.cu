@@ -132,7 +132,7 @@ extern "C" int kb_symfun_forward(const kb_symfun_params* h_params, int32_t n_cen
     else  // QUEUE: queue sweep where it applies, else the v3 sweep; AUTO / SPLIT: v3 (until the queue form wins)
       rc = kb_symfun_split_launch(P, n_centers, d_centers, nullptr, d_coords, d_species, d_nl_offsets,
                                   d_nl_indices, maxn, d_zeta, d_dz, dz_dtype, d_dz_ptr, ov,
-                                  mode == KB_SYMFUN_QUEUE ? 0 : 1, &launched, &may_overflow, st);
+                                  mode == KB_SYMFUN_QUEUE ? 0 : 2, &launched, &may_overflow, st);
     if (rc == KB_OK && launched && may_overflow)
     {
       int32_t n_over = 0;

@@ -427,7 +427,9 @@ __device__ __forceinline__ void prep_sort_slots(int n, const unsigned char* DEG,
 // =============================================================================================
 // stage 1 for one atom: centre ordinal t -> record `rec` (header n = -1 when the atom is declined)
 // =============================================================================================
-template <bool GRAD, typename TOut>
+// SOA: pair-ij table [8][NP] and pair-jk records [4][stride], stride = nrec rounded up to even (the
+// round-2 sweep gathers single fields of different neighbors: field-major tables spread them over the banks)
+template <bool GRAD, typename TOut, bool SOA = false>
 __device__ __forceinline__ void prep_atom(const kb_symfun_params& P, const SplitArgs& A, const RecLayout& L,
                                           const PrepSmem& W, int t, unsigned char* rec, int lane)
 {
@@ -455,7 +457,7 @@ __device__ __forceinline__ void prep_atom(const kb_symfun_params& P, const Split
   double* gRK = reinterpret_cast<double*>(rec + L.rk);
 
   const unsigned long long ACT =
-      prep_pairs<GRAD, TOut, false>(P, A, W, i, si, off, n, blk, zrow, gXYZ, gTJ, lane);
+      prep_pairs<GRAD, TOut, SOA>(P, A, W, i, si, off, n, blk, zrow, gXYZ, gTJ, lane);
 
   // ---- phase B: adjacency rows + per-slot lists (32-bit masks when every list fits in 32) ----
   const int nrec = NP <= 32
@@ -469,7 +471,7 @@ __device__ __forceinline__ void prep_atom(const kb_symfun_params& P, const Split
     return;
   }
 
-  prep_pair_records<false>(P, W, NP, nrec, 0, gRK, lane);
+  prep_pair_records<SOA>(P, W, NP, nrec, (nrec + 1) & ~1, gRK, lane);
 
   prep_sort_slots(n, DEG, KORD, lane);
 

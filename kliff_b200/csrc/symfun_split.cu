@@ -23,6 +23,7 @@
 // Reference: Descriptor::generate_one_atom (sym_fn.cpp:416-602), sym_d_g2 / sym_d_g4 (:627-809).
 #include "symfun_atom.cuh"
 #include "symfun_qsweep.cuh"
+#include "symfun_sweep3.cuh"
 
 #include <cstdlib>
 
@@ -31,7 +32,7 @@ namespace {
 // =============================================================================================
 // stage 1: tables
 // =============================================================================================
-template <bool GRAD, typename TOut>
+template <bool GRAD, typename TOut, bool SOA = false>
 __global__ void __launch_bounds__(PREP_WARPS * 32, KB_PREP_MIN_BLOCKS)
 symfun_prep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A, const int warp_bytes)
 {
@@ -45,7 +46,7 @@ symfun_prep_kernel(const __grid_constant__ kb_symfun_params P, const SplitArgs A
   for (int tt = A.lo + blockIdx.x * PREP_WARPS + warp; tt < A.hi; tt += stride)
   {
     const int t = A.subset ? A.subset[tt] : tt;
-    prep_atom<GRAD, TOut>(P, A, L, W, t, A.records + (size_t) (tt - A.lo) * L.bytes, lane);
+    prep_atom<GRAD, TOut, SOA>(P, A, L, W, t, A.records + (size_t) (tt - A.lo) * L.bytes, lane);
   }
 }
 
@@ -152,6 +153,7 @@ int qsweep_shape(const kb_symfun_params& P)
   return NE == 7 ? 1 : 2;
 }
 
+
 }  // namespace
 
 // Returns KB_OK and *launched = true when the parameter set is one these kernels handle.  Atoms
@@ -180,15 +182,21 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
   // variant 0: the queue sweep where it applies (fp64 blocks with gradient, shapes of set51 / set30);
   // variant 1: always the v3 sweep
   const int qshape = (variant == 0 && grad && dz_dtype == KB_F64) ? qsweep_shape(P) : 0;
+  // variant 2: the round-2 sweep (symfun_sweep3.cuh: 12 warps per SM) where it applies — gradient blocks,
+  // eight lanes per slot; KB_SWEEP3=0 keeps the round-1 sweep (A/B timing)
+  bool s3 = variant == 2 && grad && NGP == 8 && S3_CTAS >= 1;
+  if (const char* v = getenv("KB_SWEEP3")) { if (v[0] == '0') s3 = false; }
   const size_t limit = 227 * 1024, per_block_reserve = 1024;
   const size_t extra = qshape ? qsweep_extra_bytes(qshape == 1 ? QShape51::NI : QShape30::NI)
+                       : s3   ? (size_t) SC_DOUBLES * 8
                               : (size_t) SC_DOUBLES * 8 + 64 * 8;
   // record capacity: worst case when that still leaves the wanted residency, else what fits (never
   // below 45 % of the worst case: a filled sphere has ~44 % of its neighbor pairs within the cutoff)
   const int want = qshape ? KB_QSWEEP_MIN_BLOCKS : grad ? KB_SWEEP_MIN_BLOCKS : KB_SWEEP_MIN_BLOCKS_NOGRAD;
   int RC = worst;
   {
-    const size_t budget = limit / want - per_block_reserve;
+    const size_t budget = s3 ? (limit / S3_CTAS - per_block_reserve - 512) / S3_WARPS
+                             : limit / want - per_block_reserve;
     const size_t fixed = rec_layout(NP, 0).bytes + extra;
     if (fixed + 32 * (size_t) RC > budget)
     {
@@ -262,8 +270,9 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
     if (!qshape && !(pz && pz[0] == '1')) A.ang_lo = A.ang_hi = 0;
   }
 
-  int per_sm = (int) (limit / (sweep_smem + per_block_reserve));
-  if (per_sm > want) per_sm = want;
+  const size_t s3_smem = 512 + S3_WARPS * sweep_smem;
+  int per_sm = s3 ? (int) (limit / (s3_smem + per_block_reserve)) : (int) (limit / (sweep_smem + per_block_reserve));
+  if (per_sm > (s3 ? S3_CTAS : want)) per_sm = s3 ? S3_CTAS : want;
   if (const char* cap = getenv("KB_WARPS_PER_SM"))  // tuning experiments only
   {
     const int c = atoi(cap);
@@ -289,6 +298,23 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
     symfun_sweep_kernel<G, T><<<sgrid, 32, sweep_smem, st>>>(P, A);                                    \
     kb_timing_end(KB_T_SWEEP, st);                                                                     \
   } while (0)
+#define KB_S3_LAUNCH(T)                                                                                \
+  do {                                                                                                 \
+    cudaError_t e_ = cudaFuncSetAttribute(symfun_prep_kernel<true, T, true>,                           \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+                                          (int) (prep_warp * PREP_WARPS));                             \
+    if (e_ == cudaSuccess)                                                                             \
+      e_ = cudaFuncSetAttribute(symfun_sweep3_kernel<T>,                                               \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s3_smem);           \
+    if (e_ != cudaSuccess) { rc = -(int) e_; break; }                                                  \
+    kb_timing_begin(KB_T_PREP, st);                                                                    \
+    symfun_prep_kernel<true, T, true><<<pgrid, PREP_WARPS * 32, prep_warp * PREP_WARPS, st>>>(         \
+        P, A, (int) prep_warp);                                                                        \
+    kb_timing_end(KB_T_PREP, st);                                                                      \
+    kb_timing_begin(KB_T_SWEEP, st);                                                                   \
+    symfun_sweep3_kernel<T><<<sgrid, S3_WARPS * 32, s3_smem, st>>>(P, A, (int) sweep_smem);            \
+    kb_timing_end(KB_T_SWEEP, st);                                                                     \
+  } while (0)
 #define KB_QSPLIT_LAUNCH(SH)                                                                           \
   do {                                                                                                 \
     cudaError_t e_ = cudaFuncSetAttribute(symfun_prep_kernel<true, double>,                            \
@@ -306,6 +332,11 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
     symfun_qsweep_kernel<SH><<<sgrid, 64, sweep_smem, st>>>(P, A);                                     \
     kb_timing_end(KB_T_SWEEP, st);                                                                     \
   } while (0)
+  // (A pipelined form — table kernel of chunk c + 1 on a low-priority side stream under the sweep of chunk
+  // c, two sweep CTAs + two table CTAs per SM — was measured and removed: co-resident, the table kernel
+  // runs 5x slower (1.9 instead of 0.37 ms per 64k atoms) and the sweep 30 % slower, 37.6 instead of
+  // 32.0 ms per 1M atoms; both kernels live on issue slots and the shared-memory pipe.)
+  kb_timing_begin(KB_T_STAGE, st);
   for (int c = 0; c < n_chunks && rc == KB_OK; c++)
   {
     A.lo = c * chunk;
@@ -315,8 +346,11 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
     int pgrid = (cnt + PREP_WARPS - 1) / PREP_WARPS;
     if (pgrid > sms * 16) pgrid = sms * 16;
     int sgrid = sms * per_sm;
-    if (sgrid > cnt) sgrid = cnt;
-    if (qshape == 1) KB_QSPLIT_LAUNCH(QShape51);
+    if (s3) { if (sgrid > (cnt + S3_WARPS - 1) / S3_WARPS) sgrid = (cnt + S3_WARPS - 1) / S3_WARPS; }
+    else if (sgrid > cnt) sgrid = cnt;
+    if (s3 && dz_dtype == KB_F32) KB_S3_LAUNCH(float);
+    else if (s3) KB_S3_LAUNCH(double);
+    else if (qshape == 1) KB_QSPLIT_LAUNCH(QShape51);
     else if (qshape == 2) KB_QSPLIT_LAUNCH(QShape30);
     else if (!grad) KB_SPLIT_LAUNCH(false, double);
     else if (dz_dtype == KB_F32) KB_SPLIT_LAUNCH(true, float);
@@ -330,6 +364,8 @@ int kb_symfun_split_launch(const kb_symfun_params& P, int n_centers, const int32
   }
 #undef KB_SPLIT_LAUNCH
 #undef KB_QSPLIT_LAUNCH
+#undef KB_S3_LAUNCH
+  kb_timing_end(KB_T_STAGE, st);
   cudaFreeAsync(records, st);
   cudaFreeAsync(work, st);
   if (rc == KB_OK) *launched = true;

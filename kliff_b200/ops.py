@@ -386,8 +386,9 @@ def launch_count(reset=False):
 
 def kernel_timing(enable):
     """Collects the per-kernel device times recorded since the last call and switches recording
-    on/off.  Returns {"prep": (ms, launches), "sweep": (...), "fused": (...), "scatter": (...)}."""
-    ms = (C.c_double * 4)()
-    cnt = (C.c_int32 * 4)()
+    on/off.  Returns {"prep": (ms, launches), "sweep": (...), "fused": (...), "scatter": (...),
+    "stage": (...)} — "stage" brackets the whole two-stage descriptor path of a call (all chunks)."""
+    ms = (C.c_double * 5)()
+    cnt = (C.c_int32 * 5)()
     check(_lib.lib().kb_kernel_timing(int(bool(enable)), ms, cnt), "kb_kernel_timing")
-    return {name: (ms[q], cnt[q]) for q, name in enumerate(("prep", "sweep", "fused", "scatter"))}
+    return {name: (ms[q], cnt[q]) for q, name in enumerate(("prep", "sweep", "fused", "scatter", "stage"))}
