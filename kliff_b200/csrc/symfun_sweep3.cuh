@@ -46,6 +46,18 @@ __device__ __forceinline__ void sweep3_atom(const kb_symfun_params& P, const Spl
   TOut* blk = static_cast<TOut*>(A.dz) + dz_lo;
   double* zrow = A.zeta + (int64_t) t * D;
 
+  if (A.ang_hi > A.ang_lo)
+  {
+    // (KB_PREZERO=1) Zero the angular rows with full, coalesced sector writes first: the row pieces written at
+    // the flushes are 24 bytes at 8-byte alignment, and a partial write to a sector that is not in L2
+    // makes L2 fetch it from DRAM; after this pass every piece lands on a resident dirty line.
+    // (L2 cache hints — evict_last on the row stores, evict_first on the record copy — change nothing:
+    // 45.4 instead of 45.6 KB written, 29.7 instead of 31.5 KB read per atom, same time.)
+    TOut* z0 = blk + (unsigned) (A.ang_lo * row);
+    const int len = (A.ang_hi - A.ang_lo) * row;
+    for (int q = lane; q < len; q += 32) z0[q] = (TOut) 0;
+  }
+
   double csum[2][4];  // running sums over all slots of entry (4 h + ksub): x, y, z, phi
 #pragma unroll
   for (int h = 0; h < 2; h++) csum[h][0] = csum[h][1] = csum[h][2] = csum[h][3] = 0.0;
