@@ -239,6 +239,35 @@ int64_t kb_launch_count(int32_t reset);
 int kb_kernel_timing(int32_t enable, double* h_ms, int32_t* h_launches);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Owner-sorted (segmented) force assembly: the same contraction as kb_force_scatter_fwd without  */
+/* floating-point atomics — forces are bit-identical from run to run (calculator_torch.py:207-213, */
+/* 266-269; image folding of neighbor.py:260-296).                                                 */
+/* Plan (integer work, once per neighbor list): slot id of (centre t, slot s) = d_slot_ptr[t] + s   */
+/* with slot n_t = the centre itself; d_seg_src[d_seg_ptr[o] .. d_seg_ptr[o+1]) = the slot ids      */
+/* whose atom is owned by contributing atom o (image[atom] == o), ascending.                       */
+/*   kb_scatter_plan_begin  writes d_slot_ptr[n_centers+1], returns the number of slots (syncs)    */
+/*   kb_scatter_plan_finish writes d_seg_ptr[n_out+1], d_seg_src[total_slots] (syncs; KB_ERR_INVALID */
+/*                          when an image index lies outside [0, n_out))                           */
+/* kb_force_scatter_fwd_seg accumulates into d_forces[3 n_out] (caller zeroes) for a CLOSED range  */
+/* of centres (whole configurations: every slot owned by one of the n_out atoms comes from these   */
+/* centres).  For a sub-range of a larger plan pass d_slot_ptr + lo, d_seg_ptr + lo, the plan's    */
+/* d_seg_src, slot_base = slot_ptr[lo] - slot_ptr[0] and n_slots = slot_ptr[hi] - slot_ptr[lo].    */
+/* ------------------------------------------------------------------------------------------ */
+int kb_scatter_plan_begin(int32_t n_centers, const int32_t* d_centers, const int64_t* d_nl_offsets,
+                          int64_t* d_slot_ptr, int64_t* h_total_slots, void* stream);
+int kb_scatter_plan_finish(int32_t n_centers, const int32_t* d_centers, const int64_t* d_nl_offsets,
+                           const int32_t* d_nl_indices, const int32_t* d_image, int32_t n_out,
+                           const int64_t* d_slot_ptr, int64_t total_slots, int64_t* d_seg_ptr,
+                           int32_t* d_seg_src, void* stream);
+int kb_force_scatter_fwd_seg(int32_t n_centers, const int32_t* d_centers, const int64_t* d_nl_offsets,
+                             int32_t n_desc, const double* d_dEdG, const double* d_scale,
+                             const void* d_dz, int32_t dz_dtype, const int64_t* d_dz_ptr,
+                             const int64_t* d_slot_ptr, int64_t n_slots, int64_t slot_base,
+                             int32_t n_out, const int64_t* d_seg_ptr, const int32_t* d_seg_src,
+                             double* d_contrib /* scratch [3 n_slots] or NULL */, double* d_forces,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Column statistics and normalisation of the descriptor matrix — replaces np.mean / np.std and  */
 /* (zeta - mean) / stdev of Descriptor.generate_fingerprints                                     */
 /* (kliff/legacy/descriptors/descriptor.py:116-118, 187-194).  Deterministic two-stage sums.      */

@@ -61,6 +61,7 @@ EXPORTS = [
     "kb_force_scatter_fwd", "kb_force_scatter_bwd", "kb_dense_fold",
     "kb_probe_fp64_peak", "kb_probe_hbm_copy", "kb_launch_count", "kb_kernel_timing",
     "kb_moments", "kb_normalize",
+    "kb_scatter_plan_begin", "kb_scatter_plan_finish", "kb_force_scatter_fwd_seg",
     "kb_mlp_num_params", "kb_mlp_energy_grad", "kb_train_residual", "kb_mlp_param_grad", "kb_adam_step",
 ]
 
@@ -117,6 +118,9 @@ def lib():
     L.kb_kernel_timing.argtypes = [i32, C.POINTER(dbl), C.POINTER(i32)]
     L.kb_launch_count.argtypes = [i32]
     L.kb_launch_count.restype = i64
+    L.kb_scatter_plan_begin.argtypes = [i32, vp, vp, vp, C.POINTER(i64), vp]
+    L.kb_scatter_plan_finish.argtypes = [i32, vp, vp, vp, vp, i32, vp, i64, vp, vp, vp]
+    L.kb_force_scatter_fwd_seg.argtypes = [i32, vp, vp, i32, vp, vp, vp, i32, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp]
     L.kb_moments.argtypes = [i64, i32, vp, vp, vp, vp]
     L.kb_normalize.argtypes = [i64, i32, vp, vp, vp, vp, vp]
     md = C.POINTER(kb_mlp_desc)

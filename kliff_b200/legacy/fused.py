@@ -5,7 +5,7 @@ What the reference does per batch — `CalculatorTorch.compute` (calculator_torc
 micro-kernels for a 51-10-10-1 network (forward, double backward through dE/dzeta, index_add,
 repeat_interleave, Adam ...).  Here one step is nine launches of hand-written kernels on flat buffers:
 
-    forces.zero_ -> kb_mlp_energy_grad -> kb_force_scatter_fwd -> kb_train_residual
+    forces.zero_ -> kb_mlp_energy_grad -> kb_force_scatter_fwd_seg (2 launches) -> kb_train_residual
                  -> kb_force_scatter_bwd -> kb_mlp_param_grad (3 launches) -> [all-reduce] -> kb_adam_step
 
 and a whole epoch (every batch, gradient all-reduce included) is ONE CUDA graph.
@@ -145,6 +145,12 @@ class FusedTrainer:
         self.partials = torch.empty(((n + 31) // 32, self.net.P), dtype=torch.float64, device=dev)
         self._sized = n
 
+    def _slot_buffer(self, nslots):
+        """Scratch of the owner-sorted force assembly (3 doubles per slot of the largest batch)."""
+        if nslots > getattr(self, "_slots_sized", 0):
+            self.contrib = torch.empty(3 * int(nslots), dtype=torch.float64, device=self.net.dev)
+            self._slots_sized = int(nslots)
+
     # ------------------------------------------------------------------------------------------
     def step(self, c0, c1, nglobal, train):
         """One batch: this rank's configurations [c0, c1) of a global batch of `nglobal`."""
@@ -163,11 +169,14 @@ class FusedTrainer:
                 pack = P.pack_for(lo, hi)
                 F = self.F[:3 * n]
                 F.zero_()
-                check(L.kb_force_scatter_fwd(n, ops._ptr(pack["centers"]), ops._ptr(pack["offsets"]),
-                                             ops._ptr(pack["indices"]), ops._ptr(pack["image"]), pack["D"],
-                                             ops._ptr(self.dEdx), ops._ptr(pack.get("scale")), ops._ptr(pack["dz"]),
-                                             ops._dz_code(pack["dz"]), ops._ptr(pack["dz_ptr"]),
-                                             ops._ptr(F, -24 * lo), ops._stream()), "kb_force_scatter_fwd")
+                plan = pack["plan"]  # owner-sorted assembly: forces (and the loss) are bit-reproducible
+                self._slot_buffer(max(plan["n_slots"], 1))
+                check(L.kb_force_scatter_fwd_seg(
+                    n, ops._ptr(pack["centers"]), ops._ptr(pack["offsets"]), pack["D"], ops._ptr(self.dEdx),
+                    ops._ptr(pack.get("scale")), ops._ptr(pack["dz"]), ops._dz_code(pack["dz"]),
+                    ops._ptr(pack["dz_ptr"]), ops._ptr(plan["slot_ptr"]), plan["n_slots"], plan["slot_base"], n,
+                    ops._ptr(plan["seg_ptr"]), ops._ptr(plan["seg_src"]), ops._ptr(self.contrib), ops._ptr(F),
+                    ops._stream()), "kb_force_scatter_fwd_seg")
             check(L.kb_train_residual(c1 - c0, ops._ptr(self.cfg_ptr, 8 * c0), lo, ops._ptr(self.e_atom),
                                       ops._ptr(self.F) if uf else None, ops._ptr(self.e_ref, 8 * c0),
                                       ops._ptr(self.f_ref, 24 * lo) if uf else None, ops._ptr(self.w_e, 8 * c0),
@@ -205,6 +214,11 @@ class FusedTrainer:
         if g is None:
             self._buffers(max(int(self.calc._packed.cfg_ptr[c1] - self.calc._packed.cfg_ptr[c0])
                               for c0, c1, _ in batches) if batches else 1)
+            if self.use_forces and batches:
+                Pk = self.calc._packed
+                Pk.scatter_plan()
+                sp = Pk._slot_ptr_host
+                self._slot_buffer(max(int(sp[int(Pk.cfg_ptr[c1])] - sp[int(Pk.cfg_ptr[c0])]) for c0, c1, _ in batches))
             if self._pool is None:
                 # one eager warm-up step on a side stream (library handles, NCCL communicator), moving nothing
                 side = torch.cuda.Stream(device=self.net.dev)

@@ -296,12 +296,45 @@ class _ForceGather(torch.autograd.Function):
         return _ForceScatter.apply(gg, ctx.pack), None
 
 
+def scatter_plan(offsets, indices, image, n_out, centers=None, n_centers=None):
+    """Owner-sorted plan of the deterministic force assembly (kb_scatter_plan_*): returns
+    dict(slot_ptr i64[n_centers+1], seg_ptr i64[n_out+1], seg_src i32[slots], n_slots)."""
+    _need_cuda(offsets, indices, image)
+    n_centers = int(centers.shape[0]) if centers is not None else int(n_centers)
+    dev = offsets.device
+    slot_ptr = torch.empty(n_centers + 1, dtype=torch.int64, device=dev)
+    total = C.c_int64(0)
+    check(_lib.lib().kb_scatter_plan_begin(n_centers, _ptr(centers), _ptr(offsets), _ptr(slot_ptr),
+                                           C.byref(total), _stream()), "kb_scatter_plan_begin")
+    seg_ptr = torch.empty(n_out + 1, dtype=torch.int64, device=dev)
+    seg_src = torch.empty(max(total.value, 1), dtype=torch.int32, device=dev)
+    check(_lib.lib().kb_scatter_plan_finish(n_centers, _ptr(centers), _ptr(offsets), _ptr(indices), _ptr(image),
+                                            n_out, _ptr(slot_ptr), total.value, _ptr(seg_ptr), _ptr(seg_src),
+                                            _stream()), "kb_scatter_plan_finish")
+    return dict(slot_ptr=slot_ptr, seg_ptr=seg_ptr, seg_src=seg_src, n_slots=total.value)
+
+
 def _scatter_fwd(dEdG, pack):
     _need_cuda(dEdG)
     dEdG = dEdG.contiguous().to(torch.float64)
     n_centers = dEdG.shape[0]
     F = torch.zeros((pack["n_out"] * 3,), dtype=torch.float64, device=dEdG.device)
     idx = pack["indices"]
+    if pack.get("deterministic", True):
+        # owner-sorted reduction (bit-reproducible); the plan is integer work, cached with the pack
+        plan = pack.get("plan")
+        if plan is None:
+            if int(pack.get("out_base", 0)) != 0:
+                raise ValueError("a pack for a sub-range of centres needs the plan of its parent (plan=...)")
+            plan = scatter_plan(pack["offsets"], idx, pack["image"], pack["n_out"], pack.get("centers"), n_centers)
+            plan.update(slot_base=0)
+            pack["plan"] = plan
+        check(_lib.lib().kb_force_scatter_fwd_seg(
+            n_centers, _ptr(pack.get("centers")), _ptr(pack["offsets"]), pack["D"], _ptr(dEdG),
+            _ptr(pack.get("scale")), _ptr(pack["dz"]), _dz_code(pack["dz"]), _ptr(pack["dz_ptr"]),
+            _ptr(plan["slot_ptr"]), plan["n_slots"], plan["slot_base"], pack["n_out"], _ptr(plan["seg_ptr"]),
+            _ptr(plan["seg_src"]), None, _ptr(F), _stream()), "kb_force_scatter_fwd_seg")
+        return F
     check(_lib.lib().kb_force_scatter_fwd(n_centers, _ptr(pack.get("centers")), _ptr(pack["offsets"]),
                                           _ptr(idx), _ptr(pack["image"]), pack["D"], _ptr(dEdG),
                                           _ptr(pack.get("scale")), _ptr(pack["dz"]), _dz_code(pack["dz"]),

@@ -200,9 +200,21 @@ class PackedFingerprints:
     def pack_for(self, lo, hi):
         """Argument pack of the force-scatter kernels for the centre range [lo, hi) (a run of
         whole configurations).  Forces come out relative to contributing atom `lo`."""
+        plan = self.scatter_plan()
+        sp = plan["slot_ptr"]
+        sub = dict(slot_ptr=sp[lo:hi + 1], seg_ptr=plan["seg_ptr"][lo:hi + 1], seg_src=plan["seg_src"],
+                   slot_base=int(self._slot_ptr_host[lo]), n_slots=int(self._slot_ptr_host[hi] - self._slot_ptr_host[lo]))
         return dict(offsets=self.offsets, indices=self.indices, image=self.image, dz=self.dz,
                     dz_ptr=self.dz_ptr[lo:hi + 1], centers=self.centers[lo:hi], D=self.D,
-                    n_out=hi - lo, out_base=lo, scale=self.scale)
+                    n_out=hi - lo, out_base=lo, scale=self.scale, plan=sub)
+
+    def scatter_plan(self):
+        """Owner-sorted plan of the deterministic force assembly over ALL centres (built once; integer
+        work): slot ids per owner atom in ascending order (ops.scatter_plan)."""
+        if getattr(self, "_plan", None) is None:
+            self._plan = ops.scatter_plan(self.offsets, self.indices, self.image, self.n_centers, self.centers)
+            self._slot_ptr_host = self._plan["slot_ptr"].cpu().numpy()
+        return self._plan
 
     def dense_config(self, c, want_forces=True, want_stress=False):
         """The reference's dense per-configuration views (sym_fn.py:163-185)."""

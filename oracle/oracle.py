@@ -116,6 +116,10 @@ class Oracle:
         L.kref_desc_add.argtypes = [C.c_void_p, C.c_char_p, _dp, C.c_int, C.c_int]
         L.kref_desc_size.restype = C.c_int
         L.kref_desc_size.argtypes = [C.c_void_p]
+        L.kref_desc_read_file.restype = C.c_int
+        L.kref_desc_read_file.argtypes = [C.c_void_p, C.c_char_p]
+        L.kref_desc_mean_std.restype = C.c_int
+        L.kref_desc_mean_std.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.kref_desc_one_atom.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _ip, C.c_int, _dp,
                                          C.c_void_p, C.c_int]
         L.kref_desc_range.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _ip, _lp, _ip, _dp, _dp,
@@ -205,6 +209,37 @@ class Oracle:
             v = np.ascontiguousarray(v, np.float64)
             self.lib.kref_desc_add(d, names[k], v.reshape(-1), v.shape[0], v.shape[1])
         return d, D
+
+    def symfun_atoms_from_file(self, path, atoms, coords, species, offsets, indices):
+        """The reference's own parser + kernel: Descriptor::read_parameter_file (sym_fn.cpp:108-387) on
+        a `descriptor.params` file, then generate_one_atom for every atom in `atoms`.
+        -> (zeta [m, D], list of [D, n+1, 3] blocks, mean [D] | None, stdev [D] | None)."""
+        assert self.kind == "reference"
+        coords = np.ascontiguousarray(coords, np.float64).reshape(-1, 3)
+        species = np.ascontiguousarray(species, np.int32)
+        d = self.lib.kref_desc_create()
+        try:
+            err = self.lib.kref_desc_read_file(d, os.fsencode(path))
+            if err:
+                raise RuntimeError(f"read_parameter_file failed ({err}) on {path}")
+            D = self.lib.kref_desc_size(d)
+            mean = np.zeros(D); stdev = np.zeros(D)
+            has = 0
+            for q in range(D):
+                m, sd = C.c_double(0.0), C.c_double(0.0)
+                has = self.lib.kref_desc_mean_std(d, q, C.byref(m), C.byref(sd))
+                mean[q], stdev[q] = m.value, sd.value
+            zs, blocks = [], []
+            for i in atoms:
+                nb = np.ascontiguousarray(indices[offsets[i]:offsets[i + 1]], np.int32)
+                n = nb.shape[0]
+                z = np.zeros(D); g = np.zeros((D, n + 1, 3))
+                self.lib.kref_desc_one_atom(d, int(i), coords, species,
+                                            nb if n else np.zeros(1, np.int32), n, z, g.ctypes.data, 1)
+                zs.append(z); blocks.append(g)
+        finally:
+            self.lib.kref_desc_free(d)
+        return np.array(zs), blocks, (mean if has else None), (stdev if has else None)
 
     def symfun_atom(self, rcut, fams, i, coords, species, neigh, grad=True):
         """generate_one_atom: -> (zeta f64[D], dzeta f64[D, n+1, 3] | None)."""

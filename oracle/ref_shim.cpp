@@ -13,7 +13,21 @@
 #include <vector>
 
 #include "neighbor_list.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+#include <map>
+#include <numeric>
+#include <sstream>
+#include <string>
+// the parsed centring data has only `inline` accessors defined inside sym_fn.cpp (not linkable from here):
+// read the two private vectors directly.  The reference sources themselves stay untouched.
+#define private public
 #include "sym_fn.hpp"
+#undef private
+
+#include <cstdio>
 
 extern "C" {
 
@@ -106,6 +120,27 @@ void kref_desc_add(void* d, const char* name, const double* values, int rows, in
 }
 
 int kref_desc_size(void* d) { return static_cast<Descriptor*>(d)->get_num_descriptors(); }
+
+// Descriptor::read_parameter_file (sym_fn.cpp:108-387) on a `descriptor.params` text file: cutoffs,
+// species, hyper-parameter tables, and the centring / normalising data.  Returns 0 on success (the
+// reference returns `true` on a parse error), -1 when the file cannot be opened.
+int kref_desc_read_file(void* d, const char* path)
+{
+  FILE* f = std::fopen(path, "r");
+  if (!f) return -1;
+  int err = static_cast<Descriptor*>(d)->read_parameter_file(f);
+  std::fclose(f);
+  return err;
+}
+
+// mean / standard deviation of feature i as parsed (sym_fn.cpp:394-412); returns need_normalize()
+int kref_desc_mean_std(void* d, int i, double* mean, double* stdev)
+{
+  Descriptor* D = static_cast<Descriptor*>(d);
+  const bool has = D->normalize_ && i >= 0 && (size_t) i < D->feature_mean_.size();
+  if (has) { *mean = D->feature_mean_[i]; *stdev = D->feature_std_[i]; }
+  return has ? 1 : 0;
+}
 
 // zeta[D] and grad[D*3*(numnei+1)] are zeroed here, as the pybind wrapper does
 // (sym_fn_bind.cpp:49-52) before calling generate_one_atom.

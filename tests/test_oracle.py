@@ -163,3 +163,54 @@ def test_port_vs_live_reference_random():
     for o in (port, ref):
         with pytest.raises(RuntimeError):
             o.create_paddings(3.0, np.zeros((3, 3)), [1, 1, 1], bad, np.ones(3, np.int32))
+
+
+def _species_codes_as_parsed(path):
+    """Species -> code in first-appearance order of the cutoff lines, as Descriptor::read_parameter_file
+    assigns them (sym_fn.cpp:150-200)."""
+    codes = {}
+    lines = [l.split("#")[0].split() for l in open(path)]
+    lines = [l for l in lines if l]
+    nsp = int(lines[1][0])
+    for l in lines[2:2 + nsp * (nsp + 1) // 2]:
+        for s in l[:2]:
+            codes.setdefault(s, len(codes))
+    return codes
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="oracle/_ref not built (no /root/reference)")
+def test_write_kim_params_read_back_by_the_reference_parser(tmp_path):
+    """`descriptor.params` written by SymmetryFunction.write_kim_params (sym_fn.py:285-384) is parsed by
+    the reference's own Descriptor::read_parameter_file (sym_fn.cpp:108-387), and generate_one_atom on the
+    parsed object reproduces the recorded reference run (two species, three cutoffs, set51) — i.e. the file
+    carries the cutoffs, species order, every hyper-parameter and the mean / stdev without loss."""
+    from kliff_b200.legacy.descriptors import SymmetryFunction
+    g = load_golden("ref_run_sic64_set51.npz")
+    desc = SymmetryFunction({"Si-Si": 5.0, "Si-C": 4.5, "C-C": 4.0}, "cos", "set51", normalize=True,
+                            dtype=np.float64)
+    rng = np.random.default_rng(3)
+    desc.mean, desc.stdev = rng.normal(size=51), rng.uniform(0.5, 2.0, size=51)
+    desc.write_kim_params(str(tmp_path))
+    path = tmp_path / "descriptor.params"
+    codes = _species_codes_as_parsed(path)
+    assert set(codes) == {"Si", "C"}
+    n, allc, image = _full(g)
+    sym = np.where(g["z"][image] == 14, "Si", "C")
+    code = np.array([codes[s] for s in sym], np.int32)
+    ref = orc.Oracle("reference")
+    atoms = [int(a) for a in g["keep_atoms"]]
+    zeta, blocks, mean, stdev = ref.symfun_atoms_from_file(str(path), atoms, allc, code, g["nl_offsets"],
+                                                           g["nl_indices"])
+    assert zeta.shape == (len(atoms), 51)
+    # 16 significant digits in the file: parameters round-trip to <= 1 ulp, outputs to ~1e-13
+    assert rowwise_rel_err(zeta, g["zeta"][atoms]) <= 1e-12
+    for a, blk in zip(atoms, blocks):
+        assert rowwise_rel_err(blk, g[f"dz_{a}"]) <= 1e-12
+    assert np.allclose(mean, desc.mean, rtol=1e-15, atol=0) and np.allclose(stdev, desc.stdev, rtol=1e-15, atol=0)
+    # fp32 descriptors write 8 significant digits (sym_fn.py:296-299): still parsed, to that precision
+    desc32 = SymmetryFunction({"Si-Si": 5.0, "Si-C": 4.5, "C-C": 4.0}, "cos", "set51", normalize=False)
+    desc32.write_kim_params(str(tmp_path), fname="d32.params")
+    z32, _, m32, _ = ref.symfun_atoms_from_file(str(tmp_path / "d32.params"), atoms, allc, code,
+                                                g["nl_offsets"], g["nl_indices"])
+    assert m32 is None
+    assert rowwise_rel_err(z32, g["zeta"][atoms]) <= 1e-5
