@@ -261,7 +261,7 @@ class SlabDecomposition:
         if grad:
             pack = dict(offsets=offsets, indices=indices, image=image, dz=dz, dz_ptr=dz_ptr,
                         D=descriptor._params.n_desc, n_out=nl)
-        return dict(zeta=zeta, pack=pack, n_owned=n_own, n_local=nl, n_pad=int(pc.shape[0]))
+        return dict(zeta=zeta, pack=pack, n_owned=n_own, n_local=nl, n_pad=int(pc.shape[0]), coords=allc)
 
     def forces(self, dEdG_owned, fp):
         """Total forces on the owned atoms [n_owned, 3] from dE/dG of the owned atoms."""

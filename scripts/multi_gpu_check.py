@@ -148,8 +148,10 @@ def main():
     out["ok"] = bool(ok)
     if rank == 0:
         print(json.dumps(out))
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)  # no communicator teardown under live CUDA graphs (blocks until the watchdog fires)
 
 
 if __name__ == "__main__":
