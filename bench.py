@@ -805,6 +805,8 @@ def leave(world):
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
+        from kliff_b200.legacy.descriptors.descriptor import wait_for_fingerprints
+        wait_for_fingerprints()  # background writers of fingerprint files (create()) finish first
         os._exit(0)
 
 

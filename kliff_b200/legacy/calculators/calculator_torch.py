@@ -310,7 +310,12 @@ class CalculatorTorch:
             dedz_all = torch.autograd.grad(e_atom.sum(), zeta, create_graph=True)[0]
             for s, dedz in zip(batch, torch.split(dedz_all, natoms)):
                 if self.use_forces:
-                    dzf = s["dzetadr_forces"]
+                    dzf = s.get("dzetadr_forces")
+                    if dzf is None:
+                        raise CalculatorTorchError(
+                            "the fingerprints hold no `dzetadr_forces` (they were written with "
+                            "`store_gradients_on_disk = False`): forces cannot be computed from this file; "
+                            "re-create the fingerprints (reuse=False) or store the gradients")
                     if isinstance(dzf, PackedGradient):
                         dzf = torch.from_numpy(dzf.to_dense())
                     forces_config.append(self._compute_forces(dedz, dzf.to(device)))

@@ -160,22 +160,22 @@ class LossNeuralNetworkModel:
                                                   use_graph=self.use_cuda_graphs)
                 if chief:
                     self.calculator.save_model(epoch)
-            elif graphed:
-                epoch_loss = self._graphed_pass(train=True)
+            elif graphed and self._graphs is not None:
+                try:
+                    epoch_loss = self._graphed_pass(train=True)
+                except RuntimeError as e:
+                    # a capture-time failure (a layer with a host sync, a collective that cannot be
+                    # captured ...): no step of this epoch has been applied yet when the FIRST capture
+                    # fails; drop the graphs and train on eagerly with the same (capturable) optimizer
+                    if any(k[1] for k in self._graphs):
+                        raise
+                    print(f"kliff_b200: CUDA-graph capture failed ({e}); continuing with eager steps")
+                    self._graphs, self._graph_pool = None, None
+                    epoch_loss = self._eager_epoch(loader)
                 if chief:
                     self.calculator.save_model(epoch)
             else:
-                epoch_loss = 0
-                for batch in self._batches(loader):
-
-                    def closure():
-                        self.optimizer.zero_grad()
-                        loss = self._get_loss_batch(batch)
-                        loss.backward()
-                        return self._sync_gradients(loss)
-
-                    loss = self.optimizer.step(closure)
-                    epoch_loss += float(loss.detach())
+                epoch_loss = self._eager_epoch(loader)
                 if chief:
                     self.calculator.save_model(epoch)
             self.epoch_losses.append(epoch_loss)
@@ -187,6 +187,21 @@ class LossNeuralNetworkModel:
         if chief:
             print("Epoch = {:<6d}  loss = {:.10e}".format(epoch, epoch_loss))
             self.calculator.save_model(epoch, force_save=True)
+
+    def _eager_epoch(self, loader):
+        """One optimisation epoch with one optimizer.step(closure) per batch (loss.py:771-790)."""
+        epoch_loss = 0
+        for batch in self._batches(loader):
+
+            def closure():
+                self.optimizer.zero_grad()
+                loss = self._get_loss_batch(batch)
+                loss.backward()
+                return self._sync_gradients(loss)
+
+            loss = self.optimizer.step(closure)
+            epoch_loss += float(loss.detach())
+        return epoch_loss
 
     def _batches(self, loader):
         """Batches of samples.  On the vectorised route the DataLoader's per-sample collate

@@ -221,6 +221,16 @@ def test_calculator_reuse_fingerprints(workdir):
     from kliff_b200.legacy.calculators import CalculatorTorchError
     with pytest.raises(CalculatorTorchError):
         calc2.create(confs, fingerprints_filename="missing.pkl", reuse=True)
+    # large sets write the fingerprint file on a background thread; a reader waits for the writer
+    desc3 = SymmetryFunction({"Si-Si": 5.0}, "cos", "set51", normalize=True)
+    desc3.background_write_min_examples = 1
+    calc3 = CalculatorTorch(make_model(desc3))
+    calc3.create(confs, fingerprints_filename="fp_bg.pkl", fingerprints_mean_stdev_filename="ms_bg.pkl")
+    back = load_fingerprints("fp_bg.pkl")
+    first = load_fingerprints("fp.pkl")
+    assert len(back) == len(first) == 3
+    for a, b in zip(back, first):
+        assert np.array_equal(a["zeta"], b["zeta"]) and np.array_equal(a["forces"], b["forces"])
 
 
 # ------------------------------------------------------------------------------ training
