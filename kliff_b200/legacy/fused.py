@@ -216,8 +216,7 @@ class FusedTrainer:
                               for c0, c1, _ in batches) if batches else 1)
             if self.use_forces and batches:
                 Pk = self.calc._packed
-                Pk.scatter_plan()
-                sp = Pk._slot_ptr_host
+                sp = Pk.slot_ptr_host()
                 self._slot_buffer(max(int(sp[int(Pk.cfg_ptr[c1])] - sp[int(Pk.cfg_ptr[c0])]) for c0, c1, _ in batches))
             if self._pool is None:
                 # one eager warm-up step on a side stream (library handles, NCCL communicator), moving nothing

@@ -202,8 +202,13 @@ class PackedFingerprints:
         whole configurations).  Forces come out relative to contributing atom `lo`."""
         plan = self.scatter_plan()
         sp = plan["slot_ptr"]
+        if lo == 0 and hi == self.n_centers:
+            base, cnt = 0, plan["n_slots"]
+        else:
+            host = self.slot_ptr_host()
+            base, cnt = int(host[lo]), int(host[hi] - host[lo])
         sub = dict(slot_ptr=sp[lo:hi + 1], seg_ptr=plan["seg_ptr"][lo:hi + 1], seg_src=plan["seg_src"],
-                   slot_base=int(self._slot_ptr_host[lo]), n_slots=int(self._slot_ptr_host[hi] - self._slot_ptr_host[lo]))
+                   slot_base=base, n_slots=cnt)
         return dict(offsets=self.offsets, indices=self.indices, image=self.image, dz=self.dz,
                     dz_ptr=self.dz_ptr[lo:hi + 1], centers=self.centers[lo:hi], D=self.D,
                     n_out=hi - lo, out_base=lo, scale=self.scale, plan=sub)
@@ -213,8 +218,15 @@ class PackedFingerprints:
         work): slot ids per owner atom in ascending order (ops.scatter_plan)."""
         if getattr(self, "_plan", None) is None:
             self._plan = ops.scatter_plan(self.offsets, self.indices, self.image, self.n_centers, self.centers)
-            self._slot_ptr_host = self._plan["slot_ptr"].cpu().numpy()
+            self._slot_ptr_host = None
         return self._plan
+
+    def slot_ptr_host(self):
+        """Host copy of the plan's slot offsets (needed to slice the plan for a sub-range of configurations)."""
+        self.scatter_plan()
+        if self._slot_ptr_host is None:
+            self._slot_ptr_host = self._plan["slot_ptr"].cpu().numpy()
+        return self._slot_ptr_host
 
     def dense_config(self, c, want_forces=True, want_stress=False):
         """The reference's dense per-configuration views (sym_fn.py:163-185)."""
