@@ -324,6 +324,47 @@ int kb_adam_step(int32_t n_params, void* d_theta, const double* d_grad, double g
                  void* d_v, double* d_step, double lr, double beta1, double beta2, double eps,
                  int32_t dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* The same training step as six launches (csrc/train_fast.cu), for networks with n_in <= 64,   */
+/* widths <= 16 and lists of <= 84 neighbors (kb_train_fast_ok): MLP forward, force contraction,  */
+/* owner-sorted forces + residuals per configuration, adjoint gather, second-order backward +     */
+/* parameter-gradient partials, reduction (+ Adam).  Same references as above; the owner-sorted   */
+/* plan arguments are those of kb_force_scatter_fwd_seg.                                          */
+/* ------------------------------------------------------------------------------------------ */
+int kb_train_fast_ok(const kb_mlp_desc* M, int32_t maxn);
+/* e_atom[n] and, when d_contrib != NULL, the slot contributions [slots of the batch][3] (f64);
+ * d_w: scratch f64 [n_atoms][n_in] (dE/dx * scale); d_dz_ptr / d_slot_ptr: the batch's [n_atoms + 1] slices */
+int kb_train_forward(const kb_mlp_desc* M, int32_t n_atoms, const void* d_x, const void* d_theta,
+                     const double* d_scale, const void* d_dz, int32_t dz_dtype, const int64_t* d_dz_ptr,
+                     const int64_t* d_slot_ptr, double* d_e_atom, double* d_w, double* d_contrib, void* stream);
+/* kb_train_residual with the owner-sorted force sums folded in; one loss term per configuration in
+ * d_loss_cfg (no atomics); *d_step (Adam's step counter, may be NULL) is incremented.  d_contrib is read
+ * (slot contributions) and then overwritten, slot by slot, with dL/dF of the slot's owner atom: the row
+ * kb_train_backward reads. */
+int kb_train_residual_seg(int32_t n_cfg, const int64_t* d_cfg_ptr, int64_t atom0, const double* d_e_atom,
+                          const int64_t* d_seg_ptr, const int32_t* d_seg_src, int64_t slot_base,
+                          double* d_contrib, const double* d_e_ref, const double* d_f_ref,
+                          const double* d_w_e, const double* d_w_f, double inv_nglobal, int32_t use_energy,
+                          int32_t use_forces, double* d_a, double* d_gF, double* d_forces,
+                          double* d_loss_cfg, double* d_step, void* stream);
+/* d_partials [partial_rows][n_params] (f64): per-block partial parameter gradients, *h_rows_used of them
+ * written; d_gslot (dL/dF per slot, from kb_train_residual_seg) == NULL: energy-only; d_G: scratch f64
+ * [n_atoms][n_in] (dL/d(dE/dx)). */
+int kb_train_backward(const kb_mlp_desc* M, int32_t n_atoms, const void* d_x, const void* d_theta,
+                      const double* d_scale, const void* d_dz, int32_t dz_dtype, const int64_t* d_dz_ptr,
+                      const int64_t* d_slot_ptr, const double* d_gslot, const double* d_a, double* d_G,
+                      double* d_partials, int32_t partial_rows, int32_t* h_rows_used, void* stream);
+/* d_grad[0..P) = sum of the partial rows, d_grad[P] = sum of d_loss_cfg; apply_adam: Adam's update in the
+ * same launch with step number *d_step; *d_epoch_loss += d_grad[P] when not NULL. */
+int kb_train_update(const kb_mlp_desc* M, int32_t rows_used, const double* d_partials, int32_t n_cfg,
+                    const double* d_loss_cfg, double* d_grad, int32_t apply_adam, void* d_theta, void* d_m,
+                    void* d_v, const double* d_step, double lr, double beta1, double beta2, double eps,
+                    double* d_epoch_loss, void* stream);
+/* Adam on d_grad[0..P) after an all-reduce (step number *d_step, already counted); *d_epoch_loss += d_grad[P]. */
+int kb_train_adam(int32_t n_params, const double* d_grad, void* d_theta, void* d_m, void* d_v,
+                  const double* d_step, double lr, double beta1, double beta2, double eps, int32_t dtype,
+                  double* d_epoch_loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,8 @@ EXPORTS = [
     "kb_moments", "kb_normalize",
     "kb_scatter_plan_begin", "kb_scatter_plan_finish", "kb_force_scatter_fwd_seg",
     "kb_mlp_num_params", "kb_mlp_energy_grad", "kb_train_residual", "kb_mlp_param_grad", "kb_adam_step",
+    "kb_train_fast_ok", "kb_train_forward", "kb_train_residual_seg", "kb_train_backward", "kb_train_update",
+    "kb_train_adam",
 ]
 
 _lib = None
@@ -129,6 +131,14 @@ def lib():
     L.kb_train_residual.argtypes = [i32, vp, i64, vp, vp, vp, vp, vp, vp, dbl, i32, i32, vp, vp, vp, vp]
     L.kb_mlp_param_grad.argtypes = [md, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.kb_adam_step.argtypes = [i32, vp, vp, dbl, vp, vp, vp, dbl, dbl, dbl, dbl, i32, vp]
+    L.kb_train_fast_ok.argtypes = [md, i32]
+    L.kb_train_forward.argtypes = [md, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.kb_train_residual_seg.argtypes = [i32, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, dbl, i32, i32,
+                                        vp, vp, vp, vp, vp, vp]
+    L.kb_train_backward.argtypes = [md, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32,
+                                    C.POINTER(i32), vp]
+    L.kb_train_update.argtypes = [md, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, dbl, dbl, dbl, dbl, vp, vp]
+    L.kb_train_adam.argtypes = [i32, vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, i32, vp, vp]
     for name in EXPORTS:
         getattr(L, name)  # raises AttributeError when a declared symbol is missing
     _lib = L

@@ -17,6 +17,7 @@ stays on the torch route of `loss.py`.  The model's parameters become views into
 `model.state_dict()`, `save()` and `write_kim_model()` see the trained values at any time.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -129,6 +130,13 @@ class FusedTrainer:
         self._sized = 0
         self._graphs = {}
         self._pool = None
+        # four-launch form (csrc/train_fast.cu) when the network and the neighbor lists are inside its domain
+        self.fast = (os.environ.get("KB_TRAIN_FAST", "1") != "0"
+                     and _lib.lib().kb_train_fast_ok(C.byref(self.net.desc), int(P.maxn)) == 0)
+        if self.fast:
+            rows = 4 * torch.cuda.get_device_properties(dev).multi_processor_count
+            self.partials_fast = torch.empty((rows, npar), dtype=torch.float64, device=dev)
+            self.loss_cfg = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def _buffers(self, natoms):
         if natoms <= self._sized:
@@ -152,8 +160,71 @@ class FusedTrainer:
             self._slots_sized = int(nslots)
 
     # ------------------------------------------------------------------------------------------
+    def _step_fast(self, c0, c1, nglobal, train):
+        """`step` as six launches (csrc/train_fast.cu): MLP forward, contraction, forces + residuals per
+        configuration, adjoint, MLP backward + gradient partials, reduction (+ Adam when there is no all-reduce)."""
+        P = self.calc._packed
+        L = _lib.lib()
+        net, g, uf = self.net, self.grad, self.use_forces
+        lo, hi = int(P.cfg_ptr[c0]), int(P.cfg_ptr[c1])
+        n, ncfg = hi - lo, c1 - c0
+        self._buffers(max(n, 1))
+        if ncfg > self.loss_cfg.shape[0]:
+            self.loss_cfg = torch.zeros(ncfg, dtype=torch.float64, device=net.dev)
+        st = ops._stream()
+        pack = plan = None
+        x = self.x_all[lo:hi]
+        if n > 0:
+            if uf:
+                pack = P.pack_for(lo, hi)
+                plan = pack["plan"]
+                self._slot_buffer(max(plan["n_slots"], 1))
+                check(L.kb_train_forward(C.byref(net.desc), n, ops._ptr(x), ops._ptr(net.theta),
+                                         ops._ptr(pack.get("scale")), ops._ptr(pack["dz"]), ops._dz_code(pack["dz"]),
+                                         ops._ptr(pack["dz_ptr"]), ops._ptr(plan["slot_ptr"]), ops._ptr(self.e_atom),
+                                         ops._ptr(self.dEdx), ops._ptr(self.contrib), st), "kb_train_forward")
+            else:
+                check(L.kb_train_forward(C.byref(net.desc), n, ops._ptr(x), ops._ptr(net.theta), None, None, 0,
+                                         None, None, ops._ptr(self.e_atom), None, None, st), "kb_train_forward")
+        have_f = uf and n > 0
+        check(L.kb_train_residual_seg(
+            ncfg, ops._ptr(self.cfg_ptr, 8 * c0), lo, ops._ptr(self.e_atom),
+            ops._ptr(plan["seg_ptr"]) if have_f else None, ops._ptr(plan["seg_src"]) if have_f else None,
+            plan["slot_base"] if have_f else 0, ops._ptr(self.contrib) if have_f else None,
+            ops._ptr(self.e_ref, 8 * c0), ops._ptr(self.f_ref, 24 * lo) if have_f else None,
+            ops._ptr(self.w_e, 8 * c0), ops._ptr(self.w_f, 8 * c0) if have_f else None, 1.0 / nglobal,
+            int(self.use_energy), int(have_f), ops._ptr(self.a), ops._ptr(self.gF) if have_f else None,
+            ops._ptr(self.F) if have_f else None, ops._ptr(self.loss_cfg),
+            ops._ptr(self.step_count) if train else None, st), "kb_train_residual_seg")
+        rows = C.c_int32(0)
+        if train and n > 0:
+            check(L.kb_train_backward(
+                C.byref(net.desc), n, ops._ptr(x), ops._ptr(net.theta),
+                ops._ptr(pack.get("scale")) if uf else None, ops._ptr(pack["dz"]) if uf else None,
+                ops._dz_code(pack["dz"]) if uf else 0, ops._ptr(pack["dz_ptr"]) if uf else None,
+                ops._ptr(plan["slot_ptr"]) if uf else None, ops._ptr(self.contrib) if uf else None,
+                ops._ptr(self.a), ops._ptr(self.G), ops._ptr(self.partials_fast),
+                self.partials_fast.shape[0], C.byref(rows), st), "kb_train_backward")
+        from .loss import _dist
+        dist = _dist()
+        single = dist is None
+        check(L.kb_train_update(C.byref(net.desc), rows.value, ops._ptr(self.partials_fast), ncfg,
+                                ops._ptr(self.loss_cfg), ops._ptr(g), int(train and single), ops._ptr(net.theta),
+                                ops._ptr(self.m), ops._ptr(self.v), ops._ptr(self.step_count), self.lr, self.b1,
+                                self.b2, self.eps, ops._ptr(self.acc) if single else None, st), "kb_train_update")
+        if not single:
+            dist.all_reduce(g if train else g[net.P:], op=dist.ReduceOp.SUM)
+            if train:
+                check(L.kb_train_adam(net.P, ops._ptr(g), ops._ptr(net.theta), ops._ptr(self.m), ops._ptr(self.v),
+                                      ops._ptr(self.step_count), self.lr, self.b1, self.b2, self.eps, net.desc.dtype,
+                                      ops._ptr(self.acc), st), "kb_train_adam")
+            else:
+                self.acc.add_(g[net.P])
+
     def step(self, c0, c1, nglobal, train):
         """One batch: this rank's configurations [c0, c1) of a global batch of `nglobal`."""
+        if self.fast:
+            return self._step_fast(c0, c1, nglobal, train)
         P = self.calc._packed
         L = _lib.lib()
         lo, hi = int(P.cfg_ptr[c0]), int(P.cfg_ptr[c1])
