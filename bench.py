@@ -462,6 +462,10 @@ def train_epoch_probe(ncfg, dev, world=1):
             "epoch_s": t_epoch, "epoch_wall_s": t_epoch_wall, "steps_per_epoch": steps,
             "us_per_step": 1e6 * t_epoch / steps, "loss_pass_s": t_eval,
             "minimize_10_epochs_s": t_run, "fused_step": fused, "cuda_graphs": bool(loss.use_cuda_graphs),
+            "six_launch_step": bool(fused and loss._fused.fast),
+            "grad_allreduce": (None if world == 1 else
+                               "nvlink-peer (one launch with the partial reduction and Adam)"
+                               if fused and loss._fused.peer is not None else "nccl"),
             "note": "epoch_s = device time (CUDA events, max over ranks) of one optimisation epoch = one replay of "
                     "the epoch graph (batch 100: forward, forces, loss, second-order backward, gradient all-reduce, "
                     "Adam per step), graph capture and warm-up outside the timed region; minimize_10_epochs_s = "

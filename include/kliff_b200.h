@@ -365,6 +365,29 @@ int kb_train_adam(int32_t n_params, const double* d_grad, void* d_theta, void* d
                   const double* d_step, double lr, double beta1, double beta2, double eps, int32_t dtype,
                   double* d_epoch_loss, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Data-parallel form of kb_train_update (csrc/peer.cu): the gradient all-reduce over NVLink    */
+/* peer memory inside the same launch as the partial reduction and Adam — replaces               */
+/* ncclAllReduce + optimizer.step() of a sharded Loss.minimize step (loss.py:843-920).           */
+/* Every rank (one process per GPU of one node, world <= 16) allocates a workspace with          */
+/* kb_peer_alloc (cudaMalloc + IPC handle, zeroed), the 64-byte handles are exchanged by the     */
+/* host (torch.distributed), kb_peer_open maps a peer's workspace.  h_peer_ws[r] = rank r's       */
+/* workspace as mapped in this process (own pointer at [rank]).  The sum over ranks is formed in  */
+/* rank order on every rank: identical bits everywhere.  kb_peer_error reads the workspace's      */
+/* error word (non-zero: a peer did not arrive within 4 s; the step then used what was there).    */
+/* ------------------------------------------------------------------------------------------ */
+int kb_peer_ws_bytes(int32_t world, int32_t n_values, int64_t* bytes, int32_t* padded);
+int kb_peer_alloc(int64_t bytes, void** d_ptr, void* h_handle64);
+int kb_peer_open(const void* h_handle64, void** d_ptr);
+int kb_peer_close(void* d_ptr);
+int kb_peer_free(void* d_ptr);
+int kb_peer_error(const void* d_ws, int32_t* h_err, void* stream);
+int kb_train_update_peer(int32_t n_params, int32_t rows_used, const double* d_partials, int32_t n_cfg,
+                         const double* d_loss_cfg, double* d_grad, int32_t apply_adam, void* d_theta,
+                         void* d_m, void* d_v, const double* d_step, double lr, double beta1, double beta2,
+                         double eps, int32_t dtype, double* d_epoch_loss, void* const* h_peer_ws,
+                         int32_t world, int32_t rank, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,8 @@ EXPORTS = [
     "kb_mlp_num_params", "kb_mlp_energy_grad", "kb_train_residual", "kb_mlp_param_grad", "kb_adam_step",
     "kb_train_fast_ok", "kb_train_forward", "kb_train_residual_seg", "kb_train_backward", "kb_train_update",
     "kb_train_adam",
+    "kb_peer_ws_bytes", "kb_peer_alloc", "kb_peer_open", "kb_peer_close", "kb_peer_free", "kb_peer_error",
+    "kb_train_update_peer",
 ]
 
 _lib = None
@@ -139,6 +141,14 @@ def lib():
                                     C.POINTER(i32), vp]
     L.kb_train_update.argtypes = [md, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, dbl, dbl, dbl, dbl, vp, vp]
     L.kb_train_adam.argtypes = [i32, vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, i32, vp, vp]
+    L.kb_peer_ws_bytes.argtypes = [i32, i32, C.POINTER(i64), C.POINTER(i32)]
+    L.kb_peer_alloc.argtypes = [i64, C.POINTER(vp), vp]
+    L.kb_peer_open.argtypes = [vp, C.POINTER(vp)]
+    L.kb_peer_close.argtypes = [vp]
+    L.kb_peer_free.argtypes = [vp]
+    L.kb_peer_error.argtypes = [vp, C.POINTER(i32), vp]
+    L.kb_train_update_peer.argtypes = [i32, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, dbl, dbl, dbl, dbl, i32, vp,
+                                       C.POINTER(vp), i32, i32, vp]
     for name in EXPORTS:
         getattr(L, name)  # raises AttributeError when a declared symbol is missing
     _lib = L

@@ -133,12 +133,16 @@ class Descriptor:
                 example["volume"] = np.asarray(conf.get_volume(), self.dtype)
             examples.append(example)
 
+        # the writer works on its own shallow copies: callers may add keys to the returned examples while
+        # the thread is still pickling ("dictionary changed size during iteration" otherwise)
+        snapshot = [dict(e) for e in examples]
+
         def write():
             with open(fname, "ab") as f:
                 # one Pickler for the whole stream, memo cleared per example: the file is the same sequence
                 # of independent pickles that repeated pickle.dump() calls write (load_fingerprints reads it)
                 pickler = pickle.Pickler(f, protocol=pickle.HIGHEST_PROTOCOL)
-                for example in examples:
+                for example in snapshot:
                     pickler.dump(example)
                     pickler.clear_memo()
 

@@ -137,6 +137,58 @@ class FusedTrainer:
             rows = 4 * torch.cuda.get_device_properties(dev).multi_processor_count
             self.partials_fast = torch.empty((rows, npar), dtype=torch.float64, device=dev)
             self.loss_cfg = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.peer = None
+        if self.fast and os.environ.get("KB_PEER_ALLREDUCE", "1") != "0":
+            self._setup_peer()
+
+    def _setup_peer(self):
+        """Workspaces of the peer-memory gradient all-reduce (csrc/peer.cu): one cudaMalloc'ed buffer per
+        rank, mapped into every other rank of the node through CUDA IPC.  Collective; every rank ends up
+        with the same answer (`self.peer` set, or None: the NCCL all-reduce stays)."""
+        import socket
+        from .loss import _dist
+        dist = _dist()
+        if dist is None or dist.get_backend() != "nccl":
+            return
+        W, me = dist.get_world_size(), dist.get_rank()
+        L = _lib.lib()
+        nbytes, own, handle = C.c_int64(0), C.c_void_p(0), C.create_string_buffer(64)
+        ok = W <= 16 and L.kb_peer_ws_bytes(W, self.net.P + 1, C.byref(nbytes), None) == 0
+        with torch.cuda.device(self.net.dev):
+            ok = ok and L.kb_peer_alloc(nbytes.value, C.byref(own), handle) == 0
+            gathered = [None] * W
+            dist.all_gather_object(gathered, (bool(ok), handle.raw, socket.gethostname()))
+            ok = all(g[0] for g in gathered) and len({g[2] for g in gathered}) == 1
+            ptrs, opened = (C.c_void_p * W)(), []
+            if ok:
+                for r in range(W):
+                    if r == me:
+                        ptrs[r] = own.value
+                        continue
+                    p = C.c_void_p(0)
+                    if L.kb_peer_open(gathered[r][1], C.byref(p)) != 0:
+                        ok = False
+                        break
+                    ptrs[r] = p.value
+                    opened.append(p)
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.net.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag) == 1:
+                self.peer = dict(ptrs=ptrs, world=W, rank=me, own=own, opened=opened)
+                return
+            for p in opened:
+                L.kb_peer_close(p)
+            if own.value:
+                L.kb_peer_free(own)
+
+    def _check_peer(self):
+        if self.peer is None:
+            return
+        err = C.c_int32(0)
+        check(_lib.lib().kb_peer_error(self.peer["own"], C.byref(err), ops._stream()), "kb_peer_error")
+        if err.value:
+            raise RuntimeError("kliff_b200: a rank did not arrive at the peer-memory gradient exchange within 4 s "
+                               "(ranks out of step, or a peer died); KB_PEER_ALLREDUCE=0 selects the NCCL all-reduce")
 
     def _buffers(self, natoms):
         if natoms <= self._sized:
@@ -208,6 +260,15 @@ class FusedTrainer:
         from .loss import _dist
         dist = _dist()
         single = dist is None
+        if train and not single and self.peer is not None:
+            # reduction of the partials, all-reduce over NVLink peer memory and Adam in ONE launch
+            pr = self.peer
+            check(L.kb_train_update_peer(net.P, rows.value, ops._ptr(self.partials_fast), ncfg,
+                                         ops._ptr(self.loss_cfg), ops._ptr(g), 1, ops._ptr(net.theta),
+                                         ops._ptr(self.m), ops._ptr(self.v), ops._ptr(self.step_count), self.lr,
+                                         self.b1, self.b2, self.eps, net.desc.dtype, ops._ptr(self.acc), pr["ptrs"],
+                                         pr["world"], pr["rank"], st), "kb_train_update_peer")
+            return
         check(L.kb_train_update(C.byref(net.desc), rows.value, ops._ptr(self.partials_fast), ncfg,
                                 ops._ptr(self.loss_cfg), ops._ptr(g), int(train and single), ops._ptr(net.theta),
                                 ops._ptr(self.m), ops._ptr(self.v), ops._ptr(self.step_count), self.lr, self.b1,
@@ -280,7 +341,10 @@ class FusedTrainer:
         if not use_graph:
             for c0, c1, ng in batches:
                 self.step(c0, c1, ng, train)
-            return float(self.acc)
+            total = float(self.acc)
+            if train:
+                self._check_peer()
+            return total
         g = self._graphs.get(key)
         if g is None:
             self._buffers(max(int(self.calc._packed.cfg_ptr[c1] - self.calc._packed.cfg_ptr[c0])
@@ -306,7 +370,10 @@ class FusedTrainer:
                     self.step(c0, c1, ng, train)
             self._graphs[key] = g
         g.replay()
-        return float(self.acc)
+        total = float(self.acc)
+        if train:
+            self._check_peer()
+        return total
 
     def state_dict(self):
         return {"theta": self.net.theta.clone(), "m": self.m.clone(), "v": self.v.clone(),
