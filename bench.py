@@ -358,6 +358,28 @@ def run_slab_workload(args, rank, world, dev):
             "gpu_launches": r["gpu_launches"]}))
 
 
+def synthetic_configs(ncfg):
+    """The synthetic training set of the train_epoch probe: `ncfg` 64-atom diamond-Si configurations
+    (2x2x2 cells, a ~ U(5.2, 5.7), jitter 0.1 A, seed = index; reference energies/forces = N(0,1) noise)."""
+    from kliff_b200.dataset import Configuration
+    from kliff_b200.dataset.weight import Weight
+
+    basis = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0],
+                      [.25, .25, .25], [.25, .75, .75], [.75, .25, .75], [.75, .75, .25]])
+    g = np.stack(np.meshgrid(np.arange(2), np.arange(2), np.arange(2), indexing="ij"), -1).reshape(-1, 3)
+    frac = (g[:, None, :] + basis[None]).reshape(-1, 3)
+    weight = Weight(forces_weight=0.3)
+    confs = []
+    for c in range(ncfg):
+        rng = np.random.default_rng(c)
+        a = rng.uniform(5.2, 5.7)
+        pos = frac * a + rng.normal(0, 0.1, frac.shape)
+        confs.append(Configuration(cell=np.eye(3) * 2 * a, species=["Si"] * 64, coords=pos, PBC=[True] * 3,
+                                   energy=float(rng.normal()), forces=rng.normal(size=(64, 3)),
+                                   weight=weight, identifier=f"syn{c}"))
+    return confs
+
+
 def train_epoch_probe(ncfg, dev, world=1):
     """Second half of BASELINE.json's metric ("train epoch time"): synthetic set of `ncfg` 64-atom
     diamond-Si configurations (2x2x2 cells, a ~ U(5.2, 5.7), jitter 0.1 A, seed = index; reference
@@ -380,19 +402,7 @@ def train_epoch_probe(ncfg, dev, world=1):
     from kliff_b200.legacy.loss import Loss
     from kliff_b200.models import NeuralNetwork
 
-    basis = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0],
-                      [.25, .25, .25], [.25, .75, .75], [.75, .25, .75], [.75, .75, .25]])
-    g = np.stack(np.meshgrid(np.arange(2), np.arange(2), np.arange(2), indexing="ij"), -1).reshape(-1, 3)
-    frac = (g[:, None, :] + basis[None]).reshape(-1, 3)
-    weight = Weight(forces_weight=0.3)
-    confs = []
-    for c in range(ncfg):
-        rng = np.random.default_rng(c)
-        a = rng.uniform(5.2, 5.7)
-        pos = frac * a + rng.normal(0, 0.1, frac.shape)
-        confs.append(Configuration(cell=np.eye(3) * 2 * a, species=["Si"] * 64, coords=pos, PBC=[True] * 3,
-                                   energy=float(rng.normal()), forces=rng.normal(size=(64, 3)),
-                                   weight=weight, identifier=f"syn{c}"))
+    confs = synthetic_configs(ncfg)
     desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": RC}, hyperparams="set51", normalize=True)
     desc.store_gradients_on_disk = False  # GPU-resident gradients only; the pickle keeps zeta/energy/forces
     model = NeuralNetwork(desc)
@@ -412,6 +422,15 @@ def train_epoch_probe(ncfg, dev, world=1):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t)
 
+    # warm-up create() on a small set, outside the timed region: kernel modules, scratch pools, the NCCL
+    # communicator of the mean/stdev all-reduce (0.25 s on the first call of a process)
+    wdesc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": RC}, hyperparams="set51", normalize=True)
+    wdesc.store_gradients_on_disk = False
+    wmodel = NeuralNetwork(wdesc)
+    wmodel.add_layers(nn.Linear(51, 10), nn.Tanh(), nn.Linear(10, 10), nn.Tanh(), nn.Linear(10, 1))
+    CalculatorTorch(wmodel).create(confs[:min(ncfg, 64 * world)], fingerprints_filename=os.path.join(tmp, "wfp.pkl"),
+                                   fingerprints_mean_stdev_filename=os.path.join(tmp, "wms.pkl"))
+    del wmodel, wdesc
     fence()
     t0 = time.time()
     calc.create(confs, fingerprints_filename=os.path.join(tmp, "fp.pkl"),
@@ -456,10 +475,34 @@ def train_epoch_probe(ncfg, dev, world=1):
         loss.minimize(method="Adam", num_epochs=10, batch_size=100, lr=1e-3)
         torch.cuda.synchronize()
         t_run = over_ranks(time.time() - t0)
+        # the usual data-parallel alternative: batch 100 PER GPU (global batch 100 N, N times fewer steps) — the
+        # per-GPU work of a step is then what one GPU does at batch 100 instead of 1/N of it
+        per_gpu = None
+        if world > 1 and fused:
+            try:
+                loss.minimize(method="Adam", num_epochs=1, batch_size=100 * world, lr=1e-3)
+                batches = loss._fused_batches()
+                loss._fused.run_pass(batches, train=True)
+                fence()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ev[0].record()
+                for _ in range(epochs):
+                    loss._fused.run_pass(batches, train=True)
+                ev[1].record()
+                torch.cuda.synchronize()
+                tw = over_ranks(ev[0].elapsed_time(ev[1]) * 1e-3 / epochs)
+                nst = (ncfg + 100 * world - 1) // (100 * world)
+                per_gpu = {"batch_size": 100 * world, "epoch_s": tw, "steps_per_epoch": nst,
+                           "us_per_step": 1e6 * tw / nst,
+                           "note": "same set, batch 100 per GPU: a different optimisation trajectory than the "
+                                   "reference's batch_size=100, reported beside it, not instead of it"}
+            except Exception as e:  # the extra line must never cost the main one
+                per_gpu = {"error": f"{type(e).__name__}: {e}"[:200]}
     steps = (ncfg + 99) // 100
     return {"configs": ncfg, "atoms": 64 * ncfg, "n_gpus": world,
             "configs_on_rank0": len(calc.fingerprints_dataset), "create_s": t_create,
-            "epoch_s": t_epoch, "epoch_wall_s": t_epoch_wall, "steps_per_epoch": steps,
+            "epoch_s": t_epoch, "epoch_wall_s": t_epoch_wall, "full_epoch_s": t_create + t_epoch,
+            "steps_per_epoch": steps, "batch100_per_gpu": per_gpu,
             "us_per_step": 1e6 * t_epoch / steps, "loss_pass_s": t_eval,
             "minimize_10_epochs_s": t_run, "fused_step": fused, "cuda_graphs": bool(loss.use_cuda_graphs),
             "six_launch_step": bool(fused and loss._fused.fast),
@@ -471,7 +514,9 @@ def train_epoch_probe(ncfg, dev, world=1):
                     "Adam per step), graph capture and warm-up outside the timed region; minimize_10_epochs_s = "
                     "wall clock of Loss.minimize(num_epochs=10) as a user calls it (capture + 10 epochs + final "
                     "loss pass); fp32 MLP 51-10-10-1, dG/dr computed in fp64 and stored in fp32 (descriptor dtype, "
-                    "as the reference); create_s = sharded descriptors + dG/dr + normalisation"}
+                    "as the reference); create_s = sharded descriptors + dG/dr + normalisation (wall clock, max over ranks, a "
+                    "64-configuration-per-rank warm-up create() before it); full_epoch_s = create_s + epoch_s = config 5's "
+                    "'full training epoch (descriptors + forces + gradient all-reduce)'"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -34,6 +34,37 @@ void kb_timing_end(int tag, cudaStream_t st);
 
 static inline cudaStream_t kb_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (sm_90+) ---------------------------------------------------
+// A kernel launched through kb_launch_pdl may be scheduled while its predecessor in the stream is still
+// draining: everything it does before kb_grid_dep_wait() — index loads, loads of data no kernel of the
+// chain writes, shared-memory set-up — overlaps the predecessor's tail and the launch latency.  The wait
+// returns when the predecessor grid has completed and its writes are visible; it is a no-op for a kernel
+// launched the ordinary way.  The attribute is set only while the stream is being captured (the fused
+// trainer's epoch graph, where every neighbour in the chain is one of these kernels and the data read ahead
+// of the wait was written before the graph launch); eager calls keep ordinary stream order.  KB_PDL=0
+// switches it off altogether.
+#ifdef __CUDACC__
+__device__ __forceinline__ void kb_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void kb_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool kb_pdl_on(cudaStream_t st);
+template <typename... KArgs, typename... Args>
+inline cudaError_t kb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kb_pdl_on(st) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Scratch comes from the stream-ordered allocator.  Its default pool gives memory back to the
 // driver at every synchronisation (release threshold 0), which turns each *_begin call into
 // fresh cudaMalloc-class allocations (measured: 23 ms per 1M-atom neighbor build instead of 2 ms).

@@ -2,9 +2,21 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 
 static std::atomic<long long> g_launches{0};
 void kb_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool kb_pdl_on(cudaStream_t st)
+{
+  static const bool on = [] {
+    const char* e = getenv("KB_PDL");
+    return !(e && e[0] == '0');
+  }();
+  if (!on) return false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+}
 
 void kb_pool_setup()
 {

@@ -220,6 +220,8 @@ mlp_forward_kernel(const __grid_constant__ FNet N, int n, const T* __restrict__ 
 {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   T* sn = reinterpret_cast<T*>(sm_raw);
+  kb_grid_dep_launch();
+  kb_grid_dep_wait();  // theta comes from the previous step's update launch
   load_net<T>(N, theta, sn);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D = N.D;
@@ -257,8 +259,9 @@ template <typename TDz> struct PartT { typedef double type; };
 template <> struct PartT<float> { typedef float type; };
 
 template <typename TDz, int CG, int RB>
-__device__ __forceinline__ void contract_rows(const TDz* __restrict__ blk, int row, int D, const double* wrow,
-                                              int lane, double* __restrict__ out)
+__device__ __forceinline__ void contract_rows(const TDz* __restrict__ blk, int row, int D,
+                                              const double* __restrict__ wglob, double* wrow, int lane,
+                                              double* __restrict__ out)
 {
   typedef typename PartT<TDz>::type A;
   int cofs[CG];
@@ -276,6 +279,15 @@ __device__ __forceinline__ void contract_rows(const TDz* __restrict__ blk, int r
       const TDz* rp = blk + (d0 + r < D ? d0 + r : D - 1) * row;
 #pragma unroll
       for (int q = 0; q < CG; q++) v[r][q] = rp[cofs[q]];
+    }
+    if (d0 == 0)
+    {
+      // the first batch of block rows (written by no kernel of the step) is in flight before this kernel
+      // waits for its predecessor, the MLP forward launch, whose weights are fetched only now
+      kb_grid_dep_wait();
+      if (lane < D) wrow[lane] = wglob[lane];
+      if (32 + lane < D) wrow[32 + lane] = wglob[32 + lane];
+      __syncwarp();
     }
 #pragma unroll
     for (int r0 = 0; r0 < RB; r0 += 8)
@@ -310,20 +322,19 @@ contract_kernel(int n, int D, const double* __restrict__ w, const TDz* __restric
   __shared__ double wsm[TF_WARPS][TF_DP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = blockIdx.x * TF_WARPS + warp;
+  kb_grid_dep_launch();
   if (t >= n) return;
   const int64_t sl = slot_ptr[t];
   const int row = 3 * (int) (slot_ptr[t + 1] - sl);
   const TDz* blk = dz + dz_ptr[t];
   double* out = contrib + 3 * (sl - slot_ptr[0]);
-  if (lane < D) wsm[warp][lane] = w[(int64_t) t * D + lane];
-  if (32 + lane < D) wsm[warp][32 + lane] = w[(int64_t) t * D + 32 + lane];
-  __syncwarp();
+  const double* wg = w + (int64_t) t * D;
   const int ncg = (row + 31) >> 5;
-  if (ncg <= 2) contract_rows<TDz, 2, 16>(blk, row, D, wsm[warp], lane, out);
-  else if (ncg == 3) contract_rows<TDz, 3, 16>(blk, row, D, wsm[warp], lane, out);
-  else if (ncg == 4) contract_rows<TDz, 4, 8>(blk, row, D, wsm[warp], lane, out);
-  else if (ncg <= 6) contract_rows<TDz, 6, 8>(blk, row, D, wsm[warp], lane, out);
-  else contract_rows<TDz, 8, 8>(blk, row, D, wsm[warp], lane, out);
+  if (ncg <= 2) contract_rows<TDz, 2, 16>(blk, row, D, wg, wsm[warp], lane, out);
+  else if (ncg == 3) contract_rows<TDz, 3, 16>(blk, row, D, wg, wsm[warp], lane, out);
+  else if (ncg == 4) contract_rows<TDz, 4, 8>(blk, row, D, wg, wsm[warp], lane, out);
+  else if (ncg <= 6) contract_rows<TDz, 6, 8>(blk, row, D, wg, wsm[warp], lane, out);
+  else contract_rows<TDz, 8, 8>(blk, row, D, wg, wsm[warp], lane, out);
 }
 
 // =====================================================================================================
@@ -342,8 +353,13 @@ train_residual_seg_kernel(int n_cfg, const int64_t* __restrict__ cfg_ptr, int64_
 {
   __shared__ double red[RS_WARPS];
   const int c = blockIdx.x;
-  if (c == 0 && threadIdx.x == 0 && step) step[0] += 1.0;  // Adam's step counter, read by the update launch
-  if (c >= n_cfg) return;
+  kb_grid_dep_launch();
+  if (c >= n_cfg)
+  {
+    kb_grid_dep_wait();
+    if (c == 0 && threadIdx.x == 0 && step) step[0] += 1.0;
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lo = (int) (cfg_ptr[c] - atom0), hi = (int) (cfg_ptr[c + 1] - atom0);
   // everything addressable from (c, lo, hi) is requested here in one batch: this kernel is a chain of
@@ -354,6 +370,12 @@ train_residual_seg_kernel(int n_cfg, const int64_t* __restrict__ cfg_ptr, int64_
   const int64_t pre_t0 = f2 ? seg_ptr[o_second] : 0, pre_t1 = f2 ? seg_ptr[o_second + 1] : 0;
   const double we = use_energy ? w_e[c] : 0.0, eref = e_ref[c];
   const double wf = use_forces ? w_f[c] : 0.0;
+  // slot ids of the first trip: the plan is constant, so these loads too run ahead of the predecessor's end
+  int64_t pre_ia = 0, pre_ib = 0;
+  if (f1 && pre_s0 + lane < pre_s1) pre_ia = (int64_t) seg_src[pre_s0 + lane] - slot_base;
+  if (f2 && pre_t0 + lane < pre_t1) pre_ib = (int64_t) seg_src[pre_t0 + lane] - slot_base;
+  kb_grid_dep_wait();  // e_atom and the slot contributions come from the two launches before
+  if (c == 0 && threadIdx.x == 0 && step) step[0] += 1.0;  // Adam's step counter, read by the update launch
   double s = 0.0;
   for (int q = lo + threadIdx.x; q < hi; q += blockDim.x) s += e_atom[q];
   s = warp_sum(s);
@@ -383,8 +405,9 @@ train_residual_seg_kernel(int n_cfg, const int64_t* __restrict__ cfg_ptr, int64_
       for (int64_t i = lane; i < max(s1 - s0, t1 - t0); i += 32)
       {
         const bool ina = s0 + i < s1, inb = t0 + i < t1;
-        const int64_t ia = ina ? (int64_t) seg_src[s0 + i] - slot_base : 0;
-        const int64_t ib = inb ? (int64_t) seg_src[t0 + i] - slot_base : 0;
+        const bool pre = first && i == lane;
+        const int64_t ia = pre ? pre_ia : (ina ? (int64_t) seg_src[s0 + i] - slot_base : 0);
+        const int64_t ib = pre ? pre_ib : (inb ? (int64_t) seg_src[t0 + i] - slot_base : 0);
         const double* pa = contrib + 3 * ia;
         const double* pb = contrib + 3 * ib;
         const double ax = pa[0], ay = pa[1], az = pa[2], bx = pb[0], by = pb[1], bz = pb[2];
@@ -690,9 +713,9 @@ int launch_mlp_forward(const kb_mlp_desc& M, int n, const void* x, const void* t
 {
   const size_t smem = net_smem_bytes<T>();
   const int nb = min(8 * sm_count(), (n + TF_WARPS - 1) / TF_WARPS);
-  mlp_forward_kernel<T, LT><<<nb, TF_WARPS * 32, smem, st>>>(make_fnet(M), n, static_cast<const T*>(x),
-                                                            static_cast<const T*>(theta), scale, e_atom, w);
-  return KB_OK;
+  cudaError_t e = kb_launch_pdl(mlp_forward_kernel<T, LT>, dim3(nb), dim3(TF_WARPS * 32), smem, st, make_fnet(M), n,
+                                static_cast<const T*>(x), static_cast<const T*>(theta), scale, e_atom, w);
+  return e == cudaSuccess ? KB_OK : -(int) e;
 }
 
 template <typename T, int LT>
@@ -745,11 +768,11 @@ extern "C" int kb_train_forward(const kb_mlp_desc* M, int32_t n_atoms, const voi
   if (!d_contrib) return KB_OK;
   const int nb = (n_atoms + TF_WARPS - 1) / TF_WARPS;
   if (dz_dtype == KB_F32)
-    contract_kernel<float><<<nb, TF_WARPS * 32, 0, st>>>(n_atoms, M->n_in, d_w, static_cast<const float*>(d_dz),
-                                                        d_dz_ptr, d_slot_ptr, d_contrib);
+    KB_CUDA(kb_launch_pdl(contract_kernel<float>, dim3(nb), dim3(TF_WARPS * 32), 0, st, n_atoms, M->n_in, d_w,
+                          static_cast<const float*>(d_dz), d_dz_ptr, d_slot_ptr, d_contrib));
   else
-    contract_kernel<double><<<nb, TF_WARPS * 32, 0, st>>>(n_atoms, M->n_in, d_w, static_cast<const double*>(d_dz),
-                                                         d_dz_ptr, d_slot_ptr, d_contrib);
+    KB_CUDA(kb_launch_pdl(contract_kernel<double>, dim3(nb), dim3(TF_WARPS * 32), 0, st, n_atoms, M->n_in, d_w,
+                          static_cast<const double*>(d_dz), d_dz_ptr, d_slot_ptr, d_contrib));
   KB_LAUNCH_CHECK();
   return KB_OK;
 }
@@ -767,10 +790,10 @@ extern "C" int kb_train_residual_seg(int32_t n_cfg, const int64_t* d_cfg_ptr, in
   if (n_cfg > 0 && use_forces && (!d_seg_ptr || !d_seg_src || !d_contrib || !d_f_ref || !d_w_f || !d_gF || !d_forces))
     return KB_ERR_INVALID;
   if (n_cfg == 0 && !d_step) return KB_OK;
-  train_residual_seg_kernel<<<n_cfg > 0 ? n_cfg : 1, RS_WARPS * 32, 0, kb_stream(stream)>>>(
-      n_cfg, d_cfg_ptr, atom0, d_e_atom, d_seg_ptr, d_seg_src, slot_base, d_contrib, d_contrib, d_e_ref, d_f_ref, d_w_e,
-      d_w_f,
-      inv_nglobal, use_energy, use_forces, d_a, d_gF, d_forces, d_loss_cfg, d_step);
+  KB_CUDA(kb_launch_pdl(train_residual_seg_kernel, dim3(n_cfg > 0 ? n_cfg : 1), dim3(RS_WARPS * 32), 0,
+                        kb_stream(stream), n_cfg, d_cfg_ptr, atom0, d_e_atom, d_seg_ptr, d_seg_src, slot_base, d_contrib,
+                        d_contrib, d_e_ref, d_f_ref, d_w_e, d_w_f, inv_nglobal, use_energy, use_forces, d_a, d_gF,
+                        d_forces, d_loss_cfg, d_step));
   KB_LAUNCH_CHECK();
   return KB_OK;
 }

@@ -107,13 +107,20 @@ class Descriptor:
         fname = to_path(fname)
         if fname.exists():
             fname.unlink()
-        zeta_all = packed.zeta_normalized.cpu().numpy()
+        # cast on the device (fp64 -> `dtype` rounds as np.asarray(zeta, dtype) does, descriptor.py:197), so that
+        # half the bytes cross PCIe for the default float32 and the per-configuration entries are plain views
+        np_dtype = np.dtype(self.dtype)
+        zn = packed.zeta_normalized
+        if np_dtype == np.float32 and zn.dtype == torch.float64:
+            zn = zn.to(torch.float32)
+        zeta_all = zn.cpu().numpy()
+        if zeta_all.dtype != np_dtype:
+            zeta_all = zeta_all.astype(np_dtype)
         inv = packed.scale
+        ptr = np.asarray(packed.cfg_ptr).tolist()
         examples = []
         for i, conf in enumerate(configs):
-            lo, hi = packed.config_slice(i)
-            zeta = np.asarray(zeta_all[lo:hi], self.dtype)
-            example = {"configuration": conf, "zeta": zeta,
+            example = {"configuration": conf, "zeta": zeta_all[ptr[i]:ptr[i + 1]],
                        "energy": np.asarray(conf.energy, self.dtype)}
             if fit_forces:
                 if self.fingerprints_format == "dense":

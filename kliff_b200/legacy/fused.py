@@ -181,6 +181,25 @@ class FusedTrainer:
             if own.value:
                 L.kb_peer_free(own)
 
+    def release_peer(self):
+        """Give the peer-memory workspaces back (collective over the ranks that set them up): importers
+        unmap first, the owners free after a barrier — CUDA IPC forbids freeing an exported buffer that a
+        peer still has open.  The captured graphs hold the raw pointers, so they go too."""
+        if self.peer is None:
+            return
+        from .loss import _dist
+        pr, self.peer = self.peer, None
+        self._graphs = {}
+        L = _lib.lib()
+        with torch.cuda.device(self.net.dev):
+            torch.cuda.synchronize()
+            for p in pr["opened"]:
+                L.kb_peer_close(p)
+            dist = _dist()
+            if dist is not None:
+                dist.barrier()
+            L.kb_peer_free(pr["own"])
+
     def _check_peer(self):
         if self.peer is None:
             return

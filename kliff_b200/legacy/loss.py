@@ -147,6 +147,8 @@ class LossNeuralNetworkModel:
         chief = dist is None or dist.get_rank() == 0
         self.epoch_losses = []
         self._graphs, self._graph_pool, self._graph_acc = {}, None, None  # graphs belong to one optimizer
+        if self._fused is not None:
+            self._fused.release_peer()  # collective, like minimize() itself: every rank replaces its trainer here
         self._fused = self._prepare_fused(method, kwargs)
         graphed = (self._fused is None and self._graphs_possible(method, kwargs)
                    and self._prepare_graphs(method, kwargs))

