@@ -16,6 +16,8 @@
 //
 // Reference: Descriptor::generate_one_atom (sym_fn.cpp:416-602), sym_d_g4 (:744-807).
 #pragma once
+#include <type_traits>
+
 #include "symfun_atom.cuh"
 
 namespace {
@@ -65,6 +67,7 @@ __device__ __forceinline__ void sweep3_atom(const kb_symfun_params& P, const Spl
   double acc[GW][4];  // per window: x, y, z of the slot's row pieces; [3] = zeta sums, running over the atom
 #pragma unroll
   for (int e = 0; e < GW; e++) acc[e][3] = 0.0;
+#ifdef KB_S3_LEGACY
   auto sweep_step = [&](const double* sc) {
     const double2 sF = *reinterpret_cast<const double2*>(sc);  // {rij^2 + rik^2 + rjk^2, F}
 #ifdef KB_S3_EXP64
@@ -103,6 +106,93 @@ __device__ __forceinline__ void sweep3_atom(const kb_symfun_params& P, const Spl
     }
   };
 
+#else
+  // Round-2 (late) form of the step.  ncu source view of the form above (gpurun_out/s6d_sweep.ncu-rep): 28 % of the
+  // loop's warp time are fixed-latency waits on the exponential chain of the trip's FIRST step — nothing of
+  // that trip is ready to run beside it — so the exponential is taken out of the step and software-pipelined:
+  // step_E of step i + 1 is issued before the FMAs of step i, across trips too (one carried double).
+  // Fewer FP64 instructions on the way (84 -> 77 per step; alone worth < 1 %: the loop is latency-, not
+  // throughput-bound): exponential in 11 (kb_exp_tab16s); v2 = E (eta A + B) with the eta-combination formed
+  // beside the chain; the two zeta = 1 entries have C' = -+1, so their C' v1 terms are ONE running sum sv
+  // (3 additions instead of 6 FMAs) that the flush subtracts from entry 0 and adds to entry 1.  The guard of
+  // sym_fn.cpp:755-767 (C' = 0 where 1 +- cos = 0: exactly collinear triples) is decided per scratch chunk
+  // in the geometry round (warp vote): a chunk holding such an entry runs the exact form of the step.
+  double sv[3] = {0.0, 0.0, 0.0};
+  auto step_E = [&](const double* sc) { return kb_exp_tab16s(-eta * sc[0], TAB); };  // e^{-eta (rij^2+rik^2+rjk^2)}, :770
+  auto step_fma = [&](const double* sc, const double E, auto exact_tag) {
+    constexpr bool EXACT = decltype(exact_tag)::value;
+    const double eF = E * sc[1];
+    const double v1x = eF * sc[2], v1y = eF * sc[3], v1z = eF * sc[4];
+    const double v2x = E * fma(eta, sc[5], sc[8]), v2y = E * fma(eta, sc[6], sc[9]),
+                 v2z = E * fma(eta, sc[7], sc[10]);
+    const double2 c0 = *reinterpret_cast<const double2*>(sc + 12);
+    const double2 c1 = *reinterpret_cast<const double2*>(sc + 14);
+    const double2 c2 = *reinterpret_cast<const double2*>(sc + 16);
+    const double2 c3 = *reinterpret_cast<const double2*>(sc + 18);
+    const double2 d3 = *reinterpret_cast<const double2*>(sc + 20);
+    double2 d0, d1, d2;
+    d1.x = -c0.x;           d1.y = c0.y;
+    d2.x = -(c0.x * c1.x);  d2.y = c0.y * c1.y;
+    if (EXACT)
+    {
+      // C' of zeta = 1 as data: -+1, or 0 where the base vanished; sv gets nothing from this step's entries 0, 1
+      d0.x = __hiloint2double(__double2hiint(c0.x) > 0 ? 0xbff00000 : 0, 0);
+      d0.y = __hiloint2double(__double2hiint(c0.y) > 0 ? 0x3ff00000 : 0, 0);
+    }
+    else
+    {
+      d0.x = d0.y = 0.0;
+      sv[0] += v1x; sv[1] += v1y; sv[2] += v1z;
+    }
+    const double cc[GW] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, c3.x, c3.y};
+    const double dd[GW] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
+#pragma unroll
+    for (int e = 0; e < GW; e++)
+    {
+      if (EXACT || e >= 2)
+      {
+        acc[e][0] = fma(cc[e], v2x, fma(dd[e], v1x, acc[e][0]));
+        acc[e][1] = fma(cc[e], v2y, fma(dd[e], v1y, acc[e][1]));
+        acc[e][2] = fma(cc[e], v2z, fma(dd[e], v1z, acc[e][2]));
+      }
+      else
+      {
+        acc[e][0] = fma(cc[e], v2x, acc[e][0]);
+        acc[e][1] = fma(cc[e], v2y, acc[e][1]);
+        acc[e][2] = fma(cc[e], v2z, acc[e][2]);
+      }
+      acc[e][3] = fma(cc[e], eF, acc[e][3]);
+    }
+  };
+  auto sweep_chunk = [&](const double* scg, const int maxcnt, auto exact_tag) {
+    int ej = 0;
+#ifdef KB_S3_PIPE
+    // exponential of step i + 1 issued before the FMAs of step i, across trips (one carried double): measured
+    // 25.52 ms against 25.24 ms for the plain two-step trip below (1 M atoms) — the scheduler already overlaps
+    // the two steps of a trip, the carried value only lengthens live ranges
+    double E0 = step_E(scg);
+#pragma unroll 1
+    for (; ej + 1 < maxcnt; ej += 2)
+    {
+      const double E1 = step_E(scg + (ej + 1) * SCW);
+      step_fma(scg + ej * SCW, E0, exact_tag);
+      const int nx = ej + 2 < maxcnt ? ej + 2 : ej + 1;  // past the end: any valid entry, the value is not used
+      E0 = step_E(scg + nx * SCW);
+      step_fma(scg + (ej + 1) * SCW, E1, exact_tag);
+    }
+    if (ej < maxcnt) step_fma(scg + ej * SCW, E0, exact_tag);
+#else
+#pragma unroll 1
+    for (; ej + 1 < maxcnt; ej += 2)
+    {
+      step_fma(scg + ej * SCW, step_E(scg + ej * SCW), exact_tag);
+      step_fma(scg + (ej + 1) * SCW, step_E(scg + (ej + 1) * SCW), exact_tag);
+    }
+    if (ej < maxcnt) step_fma(scg + ej * SCW, step_E(scg + ej * SCW), exact_tag);
+#endif
+  };
+#endif
+
   const int nwi = (n + KPW - 1) / KPW;
   for (int wi = 0; wi < nwi; wi++)
   {
@@ -119,6 +209,7 @@ __device__ __forceinline__ void sweep3_atom(const kb_symfun_params& P, const Spl
     for (int s0 = 0; s0 < maxdeg; s0 += NGP)
     {
       double* sc = scg + g * SCW;
+      bool base_zero = false;
       if (s0 + g < degk)
       {
         // field-major tables (prep_atom<.., SOA = true>): lanes gather one field of different neighbors
@@ -154,6 +245,7 @@ __device__ __forceinline__ void sweep3_atom(const kb_symfun_params& P, const Spl
         {
           const double lam = si2 ? 1.0 : -1.0;
           double bse = fma(lam, ct, 1.0);
+          base_zero |= !(bse > 0.0);
           bse = bse > 0.0 ? bse : 0.0;  // guard of :755-767
           const double b2 = bse * bse, b3 = b2 * bse, b4 = b2 * b2, b8 = b4 * b4;
           const double b16 = b8 * b8, b15 = b8 * b4 * b3;
@@ -171,8 +263,11 @@ __device__ __forceinline__ void sweep3_atom(const kb_symfun_params& P, const Spl
       }
       const int left = maxdeg - s0;
       const int maxcnt = left < NGP ? left : NGP;  // warp-uniform
+      const bool chunk_guard = __any_sync(FULL, base_zero);
       __syncwarp();
+      (void) chunk_guard;
 
+#ifdef KB_S3_LEGACY
       int ej = 0;
 #pragma unroll 1
       for (; ej + 1 < maxcnt; ej += 2)
@@ -181,10 +276,23 @@ __device__ __forceinline__ void sweep3_atom(const kb_symfun_params& P, const Spl
         sweep_step(scg + (ej + 1) * SCW);
       }
       if (ej < maxcnt) sweep_step(scg + ej * SCW);
+#else
+      if (chunk_guard) sweep_chunk(scg, maxcnt, std::true_type());
+      else sweep_chunk(scg, maxcnt, std::false_type());
+#endif
       __syncwarp();
     }
 
     // ---- flush: rows of slot k, then the transposed reduction over the four slots of the window
+#ifndef KB_S3_LEGACY
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+    {
+      acc[0][c] -= sv[c];
+      acc[1][c] += sv[c];
+      sv[c] = 0.0;
+    }
+#endif
     if (valid_k && valid_g)
     {
       TOut* o[GW];
