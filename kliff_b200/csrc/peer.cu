@@ -14,7 +14,8 @@
 // ahead of the slowest peer (it needs that peer's row of step s + 1, which the peer sends after it has read
 // step s), so two buffers are enough.  Flags carry the step number itself (monotonic), nothing is ever reset.
 // A rank that waits longer than KB_PEER_TIMEOUT_NS gives up, records it in the workspace's error word and
-// carries on (the host checks the word after the pass), so a lost peer cannot hang the GPU.
+// carries on without waiting again in later steps (the host checks the word after the pass), so a lost
+// peer costs one timeout, not one per step of the epoch graph, and cannot hang the GPU.
 #include "common.cuh"
 
 namespace {
@@ -99,8 +100,11 @@ train_update_peer_kernel(int P, int rows, const double* __restrict__ partials, i
   }
   // ---- wait for the W rows of my own inbox
   unsigned char* mine = peers.p[me];
-  bool ok = true;
-  if (lane < W)
+  // once a wait has timed out the run is lost (the host raises after the pass): later steps of the same
+  // graph must not each wait another 4 s
+  const bool dead = *reinterpret_cast<const volatile int*>(mine) != 0;
+  bool ok = !dead;
+  if (lane < W && !dead)
   {
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(
         mine + ws_flags_off() + ((size_t) (par * W + lane) * NB + blockIdx.x) * 8);
