@@ -41,6 +41,13 @@ def _rank_suffix(filename, rank):
     return path.with_name(f"{path.stem}.rank{rank}{path.suffix}")
 
 
+def _members_file(rank_file):
+    """fingerprints.rank3.pkl -> fingerprints.rank3.members.npy: the global indices a size-balanced
+    create() gave this rank, read back by `reuse=True`."""
+    path = to_path(rank_file)
+    return path.with_name(path.stem + ".members.npy")
+
+
 def _get_device(gpu):
     """calculator_torch.py:582-594, minus the CPU branch: `gpu=False` / `None` in the reference mean
     "run on the CPU"; this package has no CPU path, so they select the current CUDA device (said once)."""
@@ -103,6 +110,7 @@ class CalculatorTorch:
         self._packed = None
         self._ref = None
         self._shard = None
+        self._shard_members = None
 
     # ------------------------------------------------------------------ create (:41-126)
     @_on_model_device
@@ -110,10 +118,16 @@ class CalculatorTorch:
                fingerprints_filename="fingerprints.pkl", fingerprints_mean_stdev_filename=None,
                reuse=False, use_welford_method=False, nprocs=1, shard_configs=None):
         """`shard_configs` (default: on whenever torch.distributed runs with more than one rank and
-        fingerprints are generated, not reused): rank r generates and keeps only configurations
-        r, r + world, r + 2 world, ... — the multi-GPU form of the reference's `parmap1` over
-        configurations (descriptor.py:234-236).  Mean / stdev are all-reduced, so every rank
-        normalises with the global statistics; `Loss` then takes each rank's members of every batch."""
+        fingerprints are generated, not reused): every rank generates and keeps only its share of the
+        configurations — the multi-GPU form of the reference's `parmap1` over configurations
+        (descriptor.py:234-236).  Mean / stdev are all-reduced, so every rank normalises with the
+        global statistics; `Loss` then takes each rank's members of every batch.
+
+        Which configurations a rank keeps: `True` / `None` / "auto" — r, r + world, ... for a uniform
+        set, and the size-balanced assignment of `kliff_b200.parallel.shard_members` (cost = atoms · n²,
+        one member per rank in every run of `world` configurations) when the estimated costs differ by
+        more than 2×; "round_robin" / "balanced" force one of the two; `False` keeps everything on
+        every rank."""
         self.configs = configs
         self.use_energy = use_energy
         self.use_forces = use_forces
@@ -123,11 +137,18 @@ class CalculatorTorch:
         desc = self.model.descriptor
         self._shard = None
         dist = _dist_active()
+        self._shard_members = None
         if dist is not None and not reuse and (shard_configs is None or shard_configs):
             r, w = dist.get_rank(), dist.get_world_size()
             self._shard = (r, w, len(configs))
-            configs = list(configs[r::w])
+            mine = self._choose_members(configs, r, w, shard_configs)
+            configs = [configs[i] for i in mine]
             fingerprints_filename = _rank_suffix(fingerprints_filename, r)
+            sidecar = _members_file(fingerprints_filename)
+            if self._shard_members is not None:
+                np.save(sidecar, self._shard_members)
+            elif sidecar.exists():
+                sidecar.unlink()  # a balanced create() of an earlier run must not be read back with these files
             if fingerprints_mean_stdev_filename is None:
                 fingerprints_mean_stdev_filename = "fingerprints_mean_and_stdev.pkl"
             if r != 0:  # rank 0 writes the file the user asked for; the others keep private copies
@@ -141,6 +162,8 @@ class CalculatorTorch:
                 if mine.exists():
                     self.fingerprints_path = mine
                     self._shard = (r, w, len(configs))
+                    if _members_file(mine).exists():  # written by a size-balanced create()
+                        self._shard_members = np.load(_members_file(mine)).astype(np.int64)
                     ms = fingerprints_mean_stdev_filename or "fingerprints_mean_and_stdev.pkl"
                     if r != 0 and _rank_suffix(ms, r).exists():
                         fingerprints_mean_stdev_filename = _rank_suffix(ms, r)
@@ -171,6 +194,30 @@ class CalculatorTorch:
         if self._packed is None:
             self._packed = self._packed_from_samples(self.fingerprints_dataset.fp)
         self._upload_references()
+
+    def _choose_members(self, configs, r, w, mode):
+        """Global indices of this rank's configurations; leaves `_shard_members` at None for the
+        strided assignment (index arithmetic) and sets it to the ascending index array otherwise."""
+        from ...parallel import config_cost, shard_members
+        mode = "auto" if mode is None or mode is True else mode
+        if mode == "round_robin":
+            return range(r, len(configs), w)
+        cut = getattr(self.model.descriptor, "cutoff", None)
+        rc = max(cut.values()) if isinstance(cut, dict) and cut else 5.0
+        parts = shard_members([config_cost(c, rc) for c in configs], w, mode)
+        if all(np.array_equal(p, np.arange(k, len(configs), w)) for k, p in enumerate(parts)):
+            return range(r, len(configs), w)
+        self._shard_members = parts[r]
+        return [int(i) for i in parts[r]]
+
+    def _shard_below(self, lo):
+        """How many of this rank's configurations have a global index below `lo` (= the position in
+        the local list where global batch boundary `lo` falls)."""
+        r, w, _ = self._shard
+        members = getattr(self, "_shard_members", None)
+        if members is None:
+            return max(0, -((r - lo) // w))  # ceil((lo - r) / w) members of r, r + w, ...
+        return int(np.searchsorted(members, lo))
 
     def _packed_from_samples(self, samples):
         """Rebuild the device store from a loaded pickle when its examples carry PackedGradient

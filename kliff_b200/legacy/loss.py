@@ -216,12 +216,13 @@ class LossNeuralNetworkModel:
             bs = self.batch_size if getattr(self, "batch_size", None) else loader.batch_size
             fp = self.calculator.fingerprints_dataset.fp
             if shard is not None:
-                # global batch [lo, hi) -> the local configurations r, r + w, ... that fall inside it:
-                # positions ceil((lo - r) / w) .. ceil((hi - r) / w) of the local list (a contiguous run)
-                r, w, n = shard
+                # global batch [lo, hi) -> this rank's configurations that fall inside it: a contiguous run
+                # of the local list (members are kept in ascending global order), see _shard_below
+                below = self.calculator._shard_below
+                n = shard[2]
                 for lo in range(0, n, bs):
                     hi = min(lo + bs, n)
-                    share = _Share(fp[max(0, -((r - lo) // w)):max(0, -((r - hi) // w))])
+                    share = _Share(fp[below(lo):below(hi)])
                     share.nglobal = hi - lo
                     yield share
                 return
@@ -350,10 +351,10 @@ class LossNeuralNetworkModel:
         shard = getattr(calc, "_shard", None)
         out = []
         if shard is not None:
-            r, w, n = shard
+            n = shard[2]
             for lo in range(0, n, bs):
                 hi = min(lo + bs, n)
-                out.append((max(0, -((r - lo) // w)), max(0, -((r - hi) // w)), hi - lo))
+                out.append((calc._shard_below(lo), calc._shard_below(hi), hi - lo))
             return out
         n = len(calc.fingerprints_dataset)
         dist = _dist()

@@ -267,3 +267,91 @@ class SlabDecomposition:
         """Total forces on the owned atoms [n_owned, 3] from dE/dG of the owned atoms."""
         f_local = ops.force_scatter(dEdG_owned, fp["pack"]).reshape(fp["n_local"], 3)
         return self.reduce_ghost_forces(f_local, fp["n_owned"])
+
+
+# ---------------------------------------------------------------------------------------------
+# Sharding by configuration (SURVEY.md §8e row 1): the multi-GPU form of kliff/parallel.py
+# ---------------------------------------------------------------------------------------------
+def _dist_world():
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def parmap1(f, X, *args, tuple_X=False, nprocs=None):
+    """`kliff.parallel.parmap1` (kliff/parallel.py:8-101) with one process per GPU instead of forked
+    host workers: same call, same return value (the list of `f(x, *args)` in the order of `X`, or
+    `f(*x, *args)` with `tuple_X=True`).
+
+    The reference forks `nprocs` workers and feeds them through queues; a CUDA context does not
+    survive a fork, and the unit of parallelism here is the rank.  Under torch.distributed with more
+    than one rank, rank r evaluates items r, r + world, ... and the results are exchanged with
+    `all_gather_object`, so every rank returns the complete list (a collective call: every rank
+    must make it with the same `X`).  In a single process the items are evaluated in order on the
+    current device.  `nprocs` is accepted for signature compatibility and not used."""
+    X = list(X)
+
+    def call(x):
+        return f(*x, *args) if tuple_X else f(x, *args)
+
+    r, w = _dist_world()
+    if w == 1:
+        return [call(x) for x in X]
+    mine = [(i, call(X[i])) for i in range(r, len(X), w)]
+    parts = [None] * w
+    dist.all_gather_object(parts, mine)
+    out = [None] * len(X)
+    for part in parts:
+        for i, y in part:
+            out[i] = y
+    return out
+
+
+# kliff/parallel.py:104-190 differs from parmap1 only in its transport (Pipe instead of Queue)
+parmap2 = parmap1
+
+
+def config_cost(conf, rc):
+    """Estimated descriptor work of one configuration, atoms · n² (the triple loop of
+    `generate_one_atom`, sym_fn.cpp:416-602, visits n(n-1)/2 pairs per atom).  n is estimated from the
+    number density without building a neighbor list: n ≈ ρ · 4/3 π rc³, capped by what a non-periodic
+    cluster can hold."""
+    natoms = int(conf.get_num_atoms())
+    cell = np.asarray(conf.cell, dtype=np.float64).reshape(3, 3)
+    vol = abs(float(np.linalg.det(cell)))
+    n = float(natoms - 1)
+    if vol > 1e-12:
+        dense = natoms / vol * (4.0 / 3.0) * np.pi * float(rc) ** 3
+        n = dense if all(bool(p) for p in conf.PBC) else min(n, dense)
+    return natoms * max(n, 1.0) ** 2
+
+
+def shard_members(costs, world, mode="auto", spread=2.0):
+    """Global indices of the configurations every rank keeps: a list of `world` ascending int64 arrays.
+
+    `round_robin`: rank r keeps r, r + world, ...  `balanced`: every run of `world` consecutive
+    configurations still gives each rank exactly ONE member (so any global batch is split into shares
+    that differ by at most one configuration, whatever the batch size), but inside a run the costliest
+    configuration goes to the rank with the smallest load so far (longest-processing-time-first over
+    the runs).  `auto` balances only when the costs differ by more than `spread` (max / min); a uniform
+    set keeps the strided form.  Deterministic in (costs, world): every rank computes the same answer
+    without communication."""
+    costs = np.asarray(costs, dtype=np.float64)
+    n = costs.shape[0]
+    if mode not in ("auto", "balanced", "round_robin"):
+        raise ValueError(f"shard mode {mode!r}: expected 'auto', 'balanced' or 'round_robin'")
+    if mode == "auto":
+        lo = float(costs.min()) if n else 0.0
+        mode = "balanced" if n and (lo <= 0.0 or float(costs.max()) / lo > spread) else "round_robin"
+    if mode == "round_robin" or world == 1:
+        return [np.arange(r, n, world, dtype=np.int64) for r in range(world)]
+    load = np.zeros(world)
+    members = [[] for _ in range(world)]
+    for g in range(0, n, world):
+        idx = np.arange(g, min(g + world, n))
+        heavy_first = idx[np.lexsort((idx, -costs[idx]))]
+        light_first = np.lexsort((np.arange(world), load))
+        for i, r in zip(heavy_first, light_first):
+            members[r].append(int(i))
+            load[r] += costs[i]
+    return [np.asarray(sorted(m), dtype=np.int64) for m in members]

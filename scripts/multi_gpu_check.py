@@ -144,7 +144,7 @@ def main():
     ok = (out["slab_zeta_relerr"] <= 1e-10 and out["slab_force_relerr"] <= 1e-10
           and out["sic_dp_loss_relerr"] <= 1e-9
           and out["dp_loss_relerr"] <= 1e-9 and out["dp_loss_relerr_batch5"] <= 1e-9
-          and out["dp_loss_relerr_replicated"] <= 1e-9 and held == len(confs[rank::world]) and held_all == 24)
+          and out["dp_loss_relerr_replicated"] <= 1e-9 and held in (len(confs) // world, -(-len(confs) // world)) and held_all == 24)
     out["ok"] = bool(ok)
     if rank == 0:
         print(json.dumps(out))
