@@ -176,6 +176,22 @@ def build_neighbors(coords, n_need, infl_dist, cutoff=None, need=None, half=Fals
     return counts, offsets, indices, maxn.value
 
 
+def build_neighbors_multi(coords, n_need, infl_dist, cutoffs, need=None, half=False):
+    """`NeighList.build(coords, influence_distance, cutoffs[k], need_neigh)` with several cutoffs
+    (neighbor_list.cpp:148-160, 210-217: one binning by the influence distance, one list per cutoff,
+    each keeping the pairs with rsq < cutoff_k²).  Returns a list of k (counts, offsets, indices, maxn)
+    tuples in the order of `cutoffs` — list k is what `get_neigh(cutoffs, k, i)` serves
+    (neighbor_list_bind.cpp:78-146).  One kb_nl_begin / kb_nl_finish pair per cutoff over the same
+    coordinates; the reference's Python layer only ever asks for one (neighbor.py:107)."""
+    cutoffs = [float(c) for c in np.atleast_1d(np.asarray(cutoffs, dtype=np.float64))]
+    if not cutoffs:
+        raise ValueError("build_neighbors_multi: at least one cutoff is needed")
+    if max(cutoffs) > float(infl_dist):
+        # the 27-cell scan only covers the influence distance (the reference would silently miss pairs)
+        raise ValueError("build_neighbors_multi: every cutoff must be <= influence_distance")
+    return [build_neighbors(coords, n_need, infl_dist, cutoff=c, need=need, half=half) for c in cutoffs]
+
+
 def batch_neighbors(cfg_ptr, cells, pbcs, coords, cutoff):
     """Paddings + neighbor lists of many configurations in one pass (kb_batch_*).
 

@@ -130,6 +130,30 @@ def test_neighbors_padding_need_neigh_and_half(dev, port):
         assert np.array_equal(hidx[hoff[a]:hoff[a + 1]], ref[ref > a])
 
 
+def test_neighbors_several_cutoffs_per_build(dev, port):
+    """nbl_build with k cutoffs (neighbor_list.cpp:148-160, 210-217): one binning by the influence
+    distance, list k keeps rsq < cutoff_k^2.  Checked against the oracle's build for every cutoff."""
+    g = load_golden("ref_run_tri30_allfam.npz")
+    infl = float(np.max(g["rcut"]))
+    full = gpu_neighbors(dev, g["cell"], g["pbc"], g["coords"], g["z"], infl)
+    allc = full["allc"]
+    need = np.zeros(allc.shape[0], np.int32)
+    need[:30] = 1
+    cutoffs = [infl, 0.8 * infl, 0.5 * infl, 0.1]
+    lists = ops.build_neighbors_multi(allc, 30, infl, cutoffs)
+    assert len(lists) == len(cutoffs)
+    for c, (counts, offsets, indices, maxn) in zip(cutoffs, lists):
+        oc, oo, oi = port.build_neighbors(allc.cpu().numpy(), infl, need, cutoff=c)
+        assert np.array_equal(counts.cpu().numpy(), oc)
+        assert np.array_equal(offsets.cpu().numpy(), oo)
+        assert np.array_equal(indices.cpu().numpy(), orc.canonical(oo, oi))
+        assert maxn == int(oc.max())
+    assert np.array_equal(lists[0][2].cpu().numpy(), full["indices"].cpu().numpy())
+    assert lists[-1][2].numel() == 0                      # nothing within 0.1 A
+    with pytest.raises(ValueError):
+        ops.build_neighbors_multi(allc, 30, infl, [2 * infl])
+
+
 def test_neighbor_errors(dev):
     bad = torch.tensor([[0.0, 0, 0], [1e-6, 0, 0], [1.0, 1, 1]], dtype=torch.float64, device=dev)
     with pytest.raises(_lib.KliffB200Error) as e:
