@@ -127,6 +127,11 @@ def test_calculator_chooses_members_and_reuse_reads_them_back(tmp_path):
     calc._shard_members = None
     assert [calc._shard_below(lo) for lo in (0, 1, 2, 5, 6, 12)] == [0, 0, 1, 1, 2, 3]
     assert list(calc._choose_members(mixed, 1, 4, "round_robin")) == [1, 5, 9] and calc._shard_members is None
+    big = [_conf(8, 5.43 + 0.0001 * (i % 7)) for i in range(3000)]   # decided on a strided sample
+    assert list(calc._choose_members(big, 2, 8, None)) == list(range(2, 3000, 8)) and calc._shard_members is None
+    big[5::3] = [_conf(64, 10.86)] * len(big[5::3])
+    mine = calc._choose_members(big, 2, 8, None)
+    assert calc._shard_members is not None and len(mine) == 3000 // 8
     f = _rank_suffix(tmp_path / "fingerprints.pkl", 3)
     assert f.name == "fingerprints.rank3.pkl" and _members_file(f).name == "fingerprints.rank3.members.npy"
 
