@@ -73,7 +73,7 @@ def main():
     every = configs_from_npz("si_varying_alat.npz", weight=Weight(forces_weight=0.3), limit=60)
     confs = [every[i] for i in range(60) if every[i].get_num_atoms() == 64][:24]
 
-    def train(distributed, shard=True, batch_size=8):
+    def train(distributed, shard=True, batch_size=8, confs=confs):
         d = SymmetryFunction({"Si-Si": 5.0}, "cos", "set51", normalize=True, dtype=np.float64)
         m = NeuralNetwork(d)
         m.add_layers(nn.Linear(51, 10), nn.Tanh(), nn.Linear(10, 10), nn.Tanh(), nn.Linear(10, 1))
@@ -81,7 +81,7 @@ def main():
         tmp = tempfile.mkdtemp()
         calc.create(confs, fingerprints_filename=os.path.join(tmp, f"fp{rank}.pkl"),
                     fingerprints_mean_stdev_filename=os.path.join(tmp, f"ms{rank}.pkl"),
-                    shard_configs=bool(distributed and shard))
+                    shard_configs=(shard if distributed else False))
         held = len(calc.fingerprints_dataset)
         m.set_save_metadata(prefix=os.path.join(tmp, "model"), start=1000, frequency=1000)
         loss = Loss(calc)
@@ -108,6 +108,14 @@ def main():
     replicated, held_all = train(True, shard=False)  # every rank keeps every configuration
     out["dp_loss_relerr_replicated"] = float(np.max(np.abs(replicated / single - 1)))
     out["dp_configs_held_replicated"] = held_all
+    # size-balanced shares on an uneven set (64- and 8-atom cells, batches that cut through the runs of `world`)
+    mixed = [c for c in every if c.get_num_atoms() == 64][:13] + [c for c in every if c.get_num_atoms() == 8][:11]
+    mixed = [mixed[i] for i in np.random.default_rng(1).permutation(len(mixed))]
+    single_m, _ = train(False, batch_size=5, confs=mixed)
+    multi_m, held_m = train(True, shard="balanced", batch_size=5, confs=mixed)
+    out["dp_loss_relerr_balanced"] = float(np.max(np.abs(multi_m / single_m - 1)))
+    out["dp_configs_held_balanced"] = held_m
+    out["dp_mixed_set"] = [int(c.get_num_atoms()) for c in mixed]
     # ---- 3. config 3: two-species SiC set, one MLP per species, configurations sharded over the ranks
     sic = configs_from_npz("sic_training_set.npz", weight=Weight(forces_weight=0.3))
 
@@ -144,6 +152,7 @@ def main():
     ok = (out["slab_zeta_relerr"] <= 1e-10 and out["slab_force_relerr"] <= 1e-10
           and out["sic_dp_loss_relerr"] <= 1e-9
           and out["dp_loss_relerr"] <= 1e-9 and out["dp_loss_relerr_batch5"] <= 1e-9
+          and out["dp_loss_relerr_balanced"] <= 1e-9
           and out["dp_loss_relerr_replicated"] <= 1e-9 and held in (len(confs) // world, -(-len(confs) // world)) and held_all == 24)
     out["ok"] = bool(ok)
     if rank == 0:
