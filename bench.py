@@ -860,4 +860,14 @@ def leave(world):
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            # a failing rank leaves at once: interpreter shutdown under live graphs / a pending collective can
+            # block until the job's time limit, and torchrun only ends the other ranks once this one is gone
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)
+        raise

@@ -25,6 +25,7 @@ import torch.nn as nn
 
 from .. import _lib, ops
 from .._lib import check
+from ..utils import capture_without_gc
 
 
 def mlp_structure(model):
@@ -384,7 +385,7 @@ class FusedTrainer:
                 self.acc.zero_()
                 self._pool = torch.cuda.graph_pool_handle()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self._pool):
+            with capture_without_gc(), torch.cuda.graph(g, pool=self._pool):
                 for c0, c1, ng in batches:
                     self.step(c0, c1, ng, train)
             self._graphs[key] = g

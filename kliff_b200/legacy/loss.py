@@ -21,6 +21,7 @@ import os
 import numpy as np
 import torch
 
+from ..utils import capture_without_gc
 from .calculators.calculator_torch import CalculatorTorch
 
 
@@ -298,7 +299,7 @@ class LossNeuralNetworkModel:
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self._graph_pool):
+            with capture_without_gc(), torch.cuda.graph(g, pool=self._graph_pool):
                 with torch.enable_grad():
                     if train:
                         self.optimizer.zero_grad(set_to_none=False)

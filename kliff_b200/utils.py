@@ -1,4 +1,6 @@
 """Small helpers shared by the plugin-API mirror (same roles as kliff/utils.py)."""
+import contextlib
+import gc
 import os
 import pickle
 import random
@@ -41,6 +43,23 @@ def pickle_dump(data, filename):
 def pickle_load(filename):
     with open(to_path(filename), "rb") as f:
         return pickle.load(f)
+
+
+@contextlib.contextmanager
+def capture_without_gc():
+    """Wrap a CUDA-graph capture: collect garbage first, then keep Python's cyclic collector off until the
+    capture has ended.  A dead reference cycle that owns CUDA graphs (an earlier Loss / trainer of this
+    process) may otherwise be collected in the middle of the capture; destroying a graph while a stream
+    captures in global mode invalidates the capture (cudaErrorStreamCaptureInvalidated — seen on one rank of
+    a 2-GPU run that built its seventh trainer).  torch.cuda.graph itself no longer collects on entry."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 def default_device():

@@ -164,4 +164,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:  # a rank that fails must leave at once (interpreter shutdown under a broken capture or a
+        import traceback   # waiting collective can block until the job's time limit), so that torchrun ends the others
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
