@@ -341,6 +341,42 @@ def test_fused_training_step_matches_torch_route(workdir, np_dtype, tol):
     assert np.allclose(outs[0], outs[1], rtol=tol)
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_graph_capture_with_an_eager_garbage_collector(workdir, fused):
+    """A process that builds one trainer after another (a 2-GPU check did, seven times) leaves dead reference
+    cycles that own CUDA graphs; collected in the middle of a later capture they invalidate it
+    (cudaErrorStreamCaptureInvalidated).  Captures therefore run with the collector held off
+    (kliff_b200.utils.capture_without_gc); here the collector is made as eager as it gets."""
+    import gc
+    weight = Weight(forces_weight=0.3)
+    confs = configs_from_npz("si_varying_alat.npz", weight=weight, limit=12)
+    saved = gc.get_threshold()
+    losses = []
+    gc.collect()
+    gc.freeze()   # what exists now is left alone: the frequent collections below only walk this test's objects
+    try:
+        for trial in range(3):
+            desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": 5.0}, hyperparams="set30", normalize=True,
+                                    dtype=np.float64)
+            model = make_model(desc)
+            model.set_save_metadata(prefix=f"./gc_{fused}_{trial}", start=10 ** 6, frequency=10 ** 6)
+            calc = CalculatorTorch(model)
+            calc.create(confs, fingerprints_filename=f"fp_gc_{trial}.pkl",
+                        fingerprints_mean_stdev_filename=f"ms_gc_{trial}.pkl")
+            loss = Loss(calc)
+            loss.use_fused = fused
+            loss._self_cycle = loss            # this trainer dies as a cycle: only the cyclic collector frees it
+            loss.minimize(method="Adam", num_epochs=2, batch_size=5, lr=0.01)
+            losses.append(np.array(loss.epoch_losses))
+            del loss, calc, model, desc
+            gc.set_threshold(20, 2, 2)         # from the second trainer on: a full collection every 80 allocations
+    finally:
+        gc.set_threshold(*saved)
+        gc.unfreeze()
+    assert all(np.all(np.isfinite(x)) for x in losses)
+    assert np.allclose(losses[0], losses[1], rtol=1e-9) and np.allclose(losses[1], losses[2], rtol=1e-9)
+
+
 def test_custom_residual_function_route(workdir):
     """A user residual_fn forces the reference's per-configuration loop (loss.py:867-920)."""
     from kliff_b200.legacy.loss import energy_residual
