@@ -47,12 +47,13 @@ def pickle_load(filename):
 
 @contextlib.contextmanager
 def capture_without_gc():
-    """Wrap a CUDA-graph capture: collect garbage first, then keep Python's cyclic collector off until the
-    capture has ended.  A dead reference cycle that owns CUDA graphs (an earlier Loss / trainer of this
-    process) may otherwise be collected in the middle of the capture; destroying a graph while a stream
-    captures in global mode invalidates the capture (cudaErrorStreamCaptureInvalidated — seen on one rank of
-    a 2-GPU run that built its seventh trainer).  torch.cuda.graph itself no longer collects on entry."""
-    gc.collect()
+    """Wrap a CUDA-graph capture: Python's cyclic collector stays off until the capture has ended.  A dead
+    reference cycle that owns CUDA graphs (an earlier Loss / trainer of this process) may otherwise be
+    collected in the middle of the capture; destroying a graph while a stream captures in global mode
+    invalidates the capture (cudaErrorStreamCaptureInvalidated — seen on one rank of a 2-GPU run that built
+    its seventh trainer; torch.cuda.graph itself no longer collects on entry).  Nothing is collected here
+    either (a full collection costs 50-100 ms beside a 20 000-configuration set): the garbage simply waits
+    for the first automatic collection after the capture."""
     was_enabled = gc.isenabled()
     gc.disable()
     try:

@@ -342,39 +342,65 @@ def test_fused_training_step_matches_torch_route(workdir, np_dtype, tol):
 
 
 @pytest.mark.parametrize("fused", [True, False])
-def test_graph_capture_with_an_eager_garbage_collector(workdir, fused):
+def test_graph_capture_with_an_eager_garbage_collector(workdir, fused, monkeypatch, request):
     """A process that builds one trainer after another (a 2-GPU check did, seven times) leaves dead reference
     cycles that own CUDA graphs; collected in the middle of a later capture they invalidate it
     (cudaErrorStreamCaptureInvalidated).  Captures therefore run with the collector held off
-    (kliff_b200.utils.capture_without_gc); here the collector is made as eager as it gets."""
+    (kliff_b200.utils.capture_without_gc).  Here an earlier trainer turns into such a cycle INSIDE the next
+    trainer's first capture, with the collector made as eager as it gets."""
     import gc
+
+    from kliff_b200.legacy.fused import FusedTrainer
+    from kliff_b200.legacy.loss import LossNeuralNetworkModel
+
     weight = Weight(forces_weight=0.3)
     confs = configs_from_npz("si_varying_alat.npz", weight=weight, limit=12)
+
+    def trained(tag):
+        desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": 5.0}, hyperparams="set30", normalize=True,
+                                dtype=np.float64)
+        model = make_model(desc)
+        model.set_save_metadata(prefix=f"./gc_{fused}_{tag}", start=10 ** 6, frequency=10 ** 6)
+        calc = CalculatorTorch(model)
+        calc.create(confs, fingerprints_filename=f"fp_gc_{tag}.pkl", fingerprints_mean_stdev_filename=f"ms_gc_{tag}.pkl")
+        loss = Loss(calc)
+        loss.use_fused = fused
+        loss.minimize(method="Adam", num_epochs=2, batch_size=5, lr=0.01)
+        return loss
+
+    def live_graphs(loss):
+        return len(loss._fused._graphs) if fused else len(loss._graphs or {})
+
     saved = gc.get_threshold()
-    losses = []
+    request.addfinalizer(lambda: (gc.set_threshold(*saved), gc.unfreeze()))
     gc.collect()
     gc.freeze()   # what exists now is left alone: the frequent collections below only walk this test's objects
-    try:
-        for trial in range(3):
-            desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": 5.0}, hyperparams="set30", normalize=True,
-                                    dtype=np.float64)
-            model = make_model(desc)
-            model.set_save_metadata(prefix=f"./gc_{fused}_{trial}", start=10 ** 6, frequency=10 ** 6)
-            calc = CalculatorTorch(model)
-            calc.create(confs, fingerprints_filename=f"fp_gc_{trial}.pkl",
-                        fingerprints_mean_stdev_filename=f"ms_gc_{trial}.pkl")
-            loss = Loss(calc)
-            loss.use_fused = fused
-            loss._self_cycle = loss            # this trainer dies as a cycle: only the cyclic collector frees it
-            loss.minimize(method="Adam", num_epochs=2, batch_size=5, lr=0.01)
-            losses.append(np.array(loss.epoch_losses))
-            del loss, calc, model, desc
-            gc.set_threshold(20, 2, 2)         # from the second trainer on: a full collection every 80 allocations
-    finally:
-        gc.set_threshold(*saved)
-        gc.unfreeze()
-    assert all(np.all(np.isfinite(x)) for x in losses)
-    assert np.allclose(losses[0], losses[1], rtol=1e-9) and np.allclose(losses[1], losses[2], rtol=1e-9)
+    first = trained("a")
+    assert live_graphs(first) >= 2           # the first trainer owns live CUDA graphs
+    ref = np.array(first.epoch_losses)
+    first._self_cycle = first                # it will die as a cycle: only the cyclic collector frees it
+    holder = [first]
+    del first
+    dropped = []
+
+    def drop_inside_capture():
+        if holder and torch.cuda.is_current_stream_capturing():
+            holder.clear()                            # garbage from here on
+            dropped.append([[i] for i in range(2000)])  # container allocations: automatic collections, if enabled
+
+    if fused:
+        orig = FusedTrainer.step
+        monkeypatch.setattr(FusedTrainer, "step", lambda self, *a, **k: (drop_inside_capture(), orig(self, *a, **k))[1])
+    else:
+        orig = LossNeuralNetworkModel._get_loss_batch
+        monkeypatch.setattr(LossNeuralNetworkModel, "_get_loss_batch",
+                            lambda self, *a, **k: (drop_inside_capture(), orig(self, *a, **k))[1])
+    gc.set_threshold(20, 2, 2)
+    second = trained("b")
+    gc.set_threshold(*saved)
+    assert dropped and not holder            # the drop happened inside a capture
+    assert live_graphs(second) >= 2          # and the capture went through (no fall-back to eager steps)
+    assert np.allclose(np.array(second.epoch_losses), ref, rtol=1e-9)   # same seed, same data
 
 
 def test_custom_residual_function_route(workdir):
