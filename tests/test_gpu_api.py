@@ -349,6 +349,7 @@ def test_graph_capture_with_an_eager_garbage_collector(workdir, fused, monkeypat
     (kliff_b200.utils.capture_without_gc).  Here an earlier trainer turns into such a cycle INSIDE the next
     trainer's first capture, with the collector made as eager as it gets."""
     import gc
+    import weakref
 
     from kliff_b200.legacy.fused import FusedTrainer
     from kliff_b200.legacy.loss import LossNeuralNetworkModel
@@ -379,6 +380,8 @@ def test_graph_capture_with_an_eager_garbage_collector(workdir, fused, monkeypat
     assert live_graphs(first) >= 2           # the first trainer owns live CUDA graphs
     ref = np.array(first.epoch_losses)
     first._self_cycle = first                # it will die as a cycle: only the cyclic collector frees it
+    freed_while_capturing = []
+    weakref.finalize(first, lambda: freed_while_capturing.append(bool(torch.cuda.is_current_stream_capturing())))
     holder = [first]
     del first
     dropped = []
@@ -386,7 +389,9 @@ def test_graph_capture_with_an_eager_garbage_collector(workdir, fused, monkeypat
     def drop_inside_capture():
         if holder and torch.cuda.is_current_stream_capturing():
             holder.clear()                            # garbage from here on
-            dropped.append([[i] for i in range(2000)])  # container allocations: automatic collections, if enabled
+            # enough surviving containers for an automatic FULL collection (CPython runs one only when the
+            # objects waiting in the middle generation exceed a quarter of the long-lived ones), if enabled
+            dropped.append([[i] for i in range(400000)])
 
     if fused:
         orig = FusedTrainer.step
@@ -399,6 +404,9 @@ def test_graph_capture_with_an_eager_garbage_collector(workdir, fused, monkeypat
     second = trained("b")
     gc.set_threshold(*saved)
     assert dropped and not holder            # the drop happened inside a capture
+    dropped.clear()
+    gc.collect()
+    assert freed_while_capturing == [False]  # the old trainer (and its graphs) went only after the capture
     assert live_graphs(second) >= 2          # and the capture went through (no fall-back to eager steps)
     assert np.allclose(np.array(second.epoch_losses), ref, rtol=1e-9)   # same seed, same data
 
