@@ -8,7 +8,7 @@ small duck-type-compatible subset: exactly the attributes the hot path reads (SU
 """
 from .configuration import Configuration, ConfigurationError, Dataset, DatasetError
 from .extxyz import read_extxyz, write_extxyz
-from .weight import Weight
+from .weight import MagnitudeInverseWeight, Weight, WeightError
 
 __all__ = [
     "Configuration",

@@ -31,11 +31,21 @@ class LossError(Exception):
         self.msg = msg
 
 
+def _w(value, like):
+    """A weight in a form the residual tensor can be multiplied by: numbers pass through; arrays
+    (`MagnitudeInverseWeight.forces_weight`, one value per force component, kliff/dataset/weight.py:178-186)
+    become tensors beside `like` — the reference multiplies a CPU tensor by the ndarray directly, which a
+    CUDA tensor cannot do."""
+    if np.ndim(value) == 0:
+        return value
+    return torch.as_tensor(np.asarray(value), dtype=like.dtype, device=like.device)
+
+
 def energy_forces_residual(identifier, natoms, weight, prediction, reference, data):
     """loss.py:37-110."""
     residual = weight.config_weight * (prediction - reference)
     residual[0] *= weight.energy_weight
-    residual[1:] *= weight.forces_weight
+    residual[1:] *= _w(weight.forces_weight, residual)
     if data["normalize_by_natoms"]:
         residual /= natoms
     return residual
@@ -51,7 +61,7 @@ def energy_residual(identifier, natoms, weight, prediction, reference, data):
 
 def forces_residual(identifier, natoms, weight, prediction, reference, data):
     """loss.py:141-166."""
-    residual = weight.config_weight * weight.forces_weight * (prediction - reference)
+    residual = weight.config_weight * _w(weight.forces_weight, prediction) * (prediction - reference)
     if data["normalize_by_natoms"]:
         residual /= natoms
     return residual
@@ -416,7 +426,19 @@ class LossNeuralNetworkModel:
     def _fast_path(self):
         calc = self.calculator
         return (self.vectorized and self._default_residual and getattr(calc, "_packed", None) is not None
-                and getattr(calc, "_ref", None) is not None and calc.use_energy and not calc.use_stress)
+                and getattr(calc, "_ref", None) is not None and calc.use_energy and not calc.use_stress
+                and self._scalar_weights())
+
+    def _scalar_weights(self):
+        """The vectorised / fused routes carry one energy and one forces weight per configuration; data-dependent
+        weights with a value per force component (MagnitudeInverseWeight) take the per-configuration route."""
+        fp = self.calculator.fingerprints_dataset.fp
+        key = (id(fp), len(fp))
+        if getattr(self, "_scalar_key", None) != key:
+            self._scalar_ok = all(np.ndim(getattr(s["configuration"].weight, name)) == 0 for s in fp
+                                  for name in ("config_weight", "energy_weight", "forces_weight"))
+            self._scalar_key = key
+        return self._scalar_ok
 
     def _get_loss_batch(self, batch, normalize=True):
         if isinstance(batch, _Share):   # sharded fingerprints: already this rank's members

@@ -411,6 +411,32 @@ def test_graph_capture_with_an_eager_garbage_collector(workdir, fused, monkeypat
     assert np.allclose(np.array(second.epoch_losses), ref, rtol=1e-9)   # same seed, same data
 
 
+def test_magnitude_inverse_weight_takes_the_per_configuration_route(workdir):
+    """MagnitudeInverseWeight (kliff/dataset/weight.py:109-232) gives one forces weight per component, so the loss
+    leaves the vectorised / fused routes for the reference's per-configuration loop (loss.py:867-920).  With c2 = 0
+    every component's weight is 1 / c1: the trajectory must equal the one of the fixed weights on the fast route."""
+    from kliff_b200.dataset import MagnitudeInverseWeight
+    runs = {}
+    for kind in ("fixed", "magnitude"):
+        confs = configs_from_npz("si_varying_alat.npz", limit=10)
+        for c in confs:
+            c.weight = (Weight(energy_weight=1 / 0.8, forces_weight=1 / 2.5) if kind == "fixed" else
+                        MagnitudeInverseWeight(weight_params={"energy_weight_params": [0.8, 0.0],
+                                                              "forces_weight_params": [2.5, 0.0]}))
+        desc = SymmetryFunction(cut_name="cos", cut_dists={"Si-Si": 5.0}, hyperparams="set30", normalize=True,
+                                dtype=np.float64)
+        model = make_model(desc)
+        model.set_save_metadata(prefix=f"./w_{kind}", start=10 ** 6, frequency=10 ** 6)
+        calc = CalculatorTorch(model)
+        calc.create(confs, fingerprints_filename=f"fp_w_{kind}.pkl", fingerprints_mean_stdev_filename=f"ms_w_{kind}.pkl")
+        loss = Loss(calc)
+        assert loss._fast_path() == (kind == "fixed")
+        loss.minimize(method="Adam", num_epochs=2, batch_size=4, lr=0.01)
+        runs[kind] = np.array(loss.epoch_losses)
+    assert isinstance(confs[0].weight.forces_weight, np.ndarray)
+    assert np.allclose(runs["fixed"], runs["magnitude"], rtol=1e-9), runs
+
+
 def test_custom_residual_function_route(workdir):
     """A user residual_fn forces the reference's per-configuration loop (loss.py:867-920)."""
     from kliff_b200.legacy.loss import energy_residual
