@@ -111,6 +111,15 @@ class Configuration:
     def metadata(self):
         return self._metadata
 
+    @property
+    def fingerprint(self):
+        """What a configuration transform left here with `copy_to_config=True` (configuration.py:455-469)."""
+        return self._fingerprint
+
+    @fingerprint.setter
+    def fingerprint(self, value):
+        self._fingerprint = value
+
     def get_num_atoms(self):
         return len(self._species)
 

@@ -6,6 +6,7 @@ the legacy zeta, and `backward(conf, dE_dZeta)` equals tensordot(dE_dZeta, dzeta
 the contributing atoms.  Here both are the same sm_100a kernels as the legacy path: forward =
 descriptor kernel, backward = the force-scatter contraction (sign flipped: it returns dE/dr)."""
 from collections import OrderedDict
+from pathlib import Path
 
 import numpy as np
 import torch
@@ -103,5 +104,62 @@ class Descriptor:
         else:
             output = descriptors
         if self.copy_to_config:
-            configuration._fingerprint = output
+            configuration.fingerprint = output
         return output
+
+    # ------------------------------------------------------------------ ConfigurationTransform interface
+    # (kliff/transforms/configuration_transforms/configuration_transform.py:58-96)
+    def transform(self, configuration):
+        return self(configuration)
+
+    def inverse(self, *args, **kargs):
+        """The reference builds a NotImplementedError without raising it (configuration_transform.py:58-67):
+        descriptors have no inverse mapping; `backward` is the vector-Jacobian product."""
+        return None
+
+    def collate_fn(self, config_list):
+        return [self(conf) for conf in config_list]
+
+    # ------------------------------------------------------------------ parameter files (descriptors.py:358-512)
+    _COLUMNS = {"g2": ("eta", "Rs"), "g3": ("kappa",), "g4": ("zeta", "lambda", "eta"),
+                "g5": ("zeta", "lambda", "eta")}
+
+    def save_descriptor_state(self, path, fname="descriptor.dat"):
+        """The text file libdescriptor re-initialises a symmetry-function descriptor from: cutoff type, the
+        species-pair cutoff table, every family with its rows of parameters, and the (identity) centring
+        block — same layout, line for line, as the reference writes (checked against a file written by the
+        reference's own function, tests/golden/descriptor_state_*.dat)."""
+        rule = "#" + "=" * 80
+        out = [rule, "# Descriptor parameters file generated by KLIFF.", rule, "",
+               f"{self.cutoff_function}  # cutoff type", "",
+               f"{len(self.species)}  # number of species", "",
+               "# species 1    species 2    cutoff"]
+        out += [f"{a}  {b}  {self.cutoff}" for a in self.species for b in self.species]
+        out += ["", rule, "# symmetry functions", rule, "",
+                f"{len(self.hyperparameters)}  # number of symmetry functions types", "",
+                "# sym_function    rows    cols"]
+        for name, rows in self.hyperparameters.items():
+            if name == "g1":
+                out += ["g1", ""]
+                continue
+            out.append(f"{name}    {len(rows)}    {len(rows[0])}")
+            cols = self._COLUMNS.get(name)
+            if cols is not None:
+                out += ["    ".join(str(row[c]) for c in cols) + "    # " + "  ".join(cols) for row in rows]
+                out.append("")
+        out += [rule, "# Preprocessing data to center and normalize", rule,
+                "center_and_normalize  True", "",
+                f"{self.width}   # descriptor size", "# mean", "0.0 ", "", "# standard deviation", "1.0 ", ""]
+        Path(path, fname).write_text("\n".join(out) + "\n")
+
+    def export_kim_model(self, path, model):
+        """`kim_model.param` of the reference's TorchML driver export (descriptors.py:484-512)."""
+        blocks = [("Number of elements", [str(len(self.species)), " ".join(self.species)]),
+                  ("Preprocessing kind", ["Descriptor"]),
+                  ("Cutoff distance", [str(self.cutoff)]),
+                  ("Model", [str(model)]),
+                  ("Returns Forces", ["False"]),
+                  ("Number of inputs", ["1"])]
+        text = "".join(f"# {title}\n" + "".join(v + "\n" for v in values) + "\n" for title, values in blocks)
+        text += f"# Any descriptors?\n{self.descriptor_name}\n"
+        Path(path, "kim_model.param").write_text(text)

@@ -114,3 +114,36 @@ def test_array_weights_leave_the_vectorised_route():
     loss.calculator = _Calc([{"configuration": _config(Weight(), seed=0)},
                              {"configuration": _config(MagnitudeInverseWeight(), seed=1)}])
     assert not loss._scalar_weights()
+
+
+# ------------------------------------------------------------------ new-API Descriptor: host-side writers
+def test_descriptor_state_and_kim_param_files_equal_the_reference_writers(tmp_path):
+    """`Descriptor.save_descriptor_state` / `export_kim_model`
+    (kliff/transforms/configuration_transforms/descriptors.py:358-512) against files written by the reference's
+    own functions (tests/golden/make_descriptor_state_golden.py)."""
+    import os
+    from collections import OrderedDict
+
+    from conftest import GOLDEN
+    from kliff_b200.transforms.configuration_transforms.descriptors import Descriptor
+
+    d30 = Descriptor(cutoff=5.0, species=["Si"], descriptor="SymmetryFunctions", hyperparameters="set30")
+    d30.save_descriptor_state(tmp_path, "a.dat")
+    assert (tmp_path / "a.dat").read_text() == open(os.path.join(GOLDEN, "descriptor_state_set30.dat")).read()
+    custom = OrderedDict([
+        ("g1", None),
+        ("g2", [{"eta": 0.0035710676725828126, "Rs": 0.0}, {"eta": 0.03571067672582813, "Rs": 1.5}]),
+        ("g3", [{"kappa": 0.3}, {"kappa": 1.25}]),
+        ("g4", [{"zeta": 1, "lambda": -1, "eta": 0.00035710676725828126}, {"zeta": 2.5, "lambda": 0.5, "eta": 0.02}]),
+        ("g5", [{"zeta": 4, "lambda": 1, "eta": 0.001}]),
+    ])
+    dc = Descriptor(cutoff=4.5, species=["Si", "C"], descriptor="SymmetryFunctions", hyperparameters=custom)
+    assert dc.width == 8
+    dc.save_descriptor_state(tmp_path)
+    assert (tmp_path / "descriptor.dat").read_text() == open(os.path.join(GOLDEN, "descriptor_state_custom.dat")).read()
+    dc.export_kim_model(str(tmp_path), "model.pt")
+    assert (tmp_path / "kim_model.param").read_text() == open(os.path.join(GOLDEN, "kim_model_param.txt")).read()
+    assert dc.inverse() is None and dc.copy_to_config is False
+    conf = _config(Weight())
+    conf.fingerprint = "x"
+    assert conf.fingerprint == "x"
