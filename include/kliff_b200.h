@@ -227,6 +227,11 @@ int kb_dense_fold(int32_t n_centers, const int32_t* d_centers, const int64_t* d_
 /* ------------------------------------------------------------------------------------------ */
 int kb_probe_fp64_peak(double* h_tflops, void* stream);
 int kb_probe_hbm_copy(size_t bytes, double* h_gbs, void* stream);
+/* Returns the scratch the library's stream-ordered allocations have cached (cudaMallocAsync on the
+ * device's default pool, kept across calls so that repeated passes do not re-allocate) to the driver,
+ * down to keep_bytes; synchronises the device.  Optional: call it after a large descriptor pass when
+ * another allocator in the process (torch) needs the memory. */
+int kb_pool_trim(size_t keep_bytes);
 /* Number of kernels this library has launched in this process (reset != 0 zeroes it). */
 int64_t kb_launch_count(int32_t reset);
 /* Per-kernel device times of the descriptor stage, measured with CUDA events on the launching

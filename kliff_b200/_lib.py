@@ -59,7 +59,7 @@ EXPORTS = [
     "kb_batch_begin", "kb_batch_neighbors", "kb_batch_finish", "kb_batch_destroy",
     "kb_symfun_block_offsets", "kb_symfun_forward",
     "kb_force_scatter_fwd", "kb_force_scatter_bwd", "kb_dense_fold",
-    "kb_probe_fp64_peak", "kb_probe_hbm_copy", "kb_launch_count", "kb_kernel_timing",
+    "kb_probe_fp64_peak", "kb_probe_hbm_copy", "kb_pool_trim", "kb_launch_count", "kb_kernel_timing",
     "kb_moments", "kb_normalize",
     "kb_scatter_plan_begin", "kb_scatter_plan_finish", "kb_force_scatter_fwd_seg",
     "kb_mlp_num_params", "kb_mlp_energy_grad", "kb_train_residual", "kb_mlp_param_grad", "kb_adam_step",
@@ -120,6 +120,7 @@ def lib():
     L.kb_probe_fp64_peak.argtypes = [C.POINTER(dbl), vp]
     L.kb_probe_hbm_copy.argtypes = [C.c_size_t, C.POINTER(dbl), vp]
     L.kb_kernel_timing.argtypes = [i32, C.POINTER(dbl), C.POINTER(i32)]
+    L.kb_pool_trim.argtypes = [C.c_size_t]
     L.kb_launch_count.argtypes = [i32]
     L.kb_launch_count.restype = i64
     L.kb_scatter_plan_begin.argtypes = [i32, vp, vp, vp, C.POINTER(i64), vp]

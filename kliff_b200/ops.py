@@ -428,6 +428,11 @@ def probe_hbm_copy(nbytes=1 << 30):
     return v.value
 
 
+def pool_trim(keep_bytes=0):
+    """Give the library's cached scratch (stream-ordered pool) back to the driver; synchronises the device."""
+    check(_lib.lib().kb_pool_trim(int(keep_bytes)), "kb_pool_trim")
+
+
 def launch_count(reset=False):
     """Kernels launched by libkliff_b200 in this process so far."""
     return int(_lib.lib().kb_launch_count(1 if reset else 0))
