@@ -31,6 +31,13 @@ def test_library_exports_every_declared_symbol(built):
     assert built.kb_error_string(1).decode().startswith("reference error")
 
 
+def test_integration_notes_name_every_entry_point():
+    """INTEGRATION.md maps each C-ABI entry point to the reference interface it replaces."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [e for e in _lib.EXPORTS if e not in text and not (e.startswith("kb_probe_") and "kb_probe_*" in text)]
+    assert not missing, missing
+
+
 def test_struct_layout_matches_header(built):
     """sizeof(kb_symfun_params) computed from the header's array bounds."""
     S, T, G, W = 8, 64, 32, 8
